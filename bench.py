@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — EM throughput of the PoissonGPLVMJump1D hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference --steps K --warmup W    # restated reference on the host CPU
+
+A "step" is ONE EM iteration (sufficient statistics -> Adam M-step -> emission ->
+forward -> backward) over the whole synthetic spike matrix of the workload
+(default: BASELINE.json configs[3], N=500 neurons, K=400 latent bins, T=1e6 bins).
+`value` = T * steps / device time with the spikes resident in HBM;
+`e2e`   = T * n_iter / wall time of a full `fit_em` call on HOST arrays (H2D of the
+          spikes and D2H of every result array inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, K, T, tuning_lengthscale, movement_variance)
+    "readme": (30, 100, 1000, 10.0, 1.0),
+    "session": (200, 100, 100000, 10.0, 1.0),
+    "headline": (500, 400, 1000000, 10.0, 1.0),
+    "stress": (300, 2000, 1000000, 10.0, 1.0),
+}
+METRIC = "EM time-bins x iters/s"
+UNIT = "bins*iters/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the restated reference (oracle/ref_numpy.py, fp32, reference operation order) on the host
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(N, K, ls, mv, sample_T, n_steps, n_warm, full_T, seed=0):
+    """Times EM iterations of the NumPy restatement on a bounded sample of the workload (sample_T bins
+    of the same synthetic process).  The E-step and the statistics GEMM cost is linear in T (reference
+    chunk loop, decoder.py:283-324); the Adam M-step is T-independent.  Returns the rate extrapolated
+    to the full workload, T / (t_mstep + (T / sample_T) * t_estep_and_stats), and the measured parts."""
+    from oracle import ref_numpy as ref
+    from poor_man_gplvm_b200.synthetic import make_dataset
+    from poor_man_gplvm_b200 import gp_kernel as gpk
+
+    d = make_dataset(sample_T, N, K, seed=seed)
+    basis = gpk.generate_basis(ls, K)
+    rng = np.random.default_rng(seed + 1)
+    params = rng.standard_normal((basis.shape[1], N)).astype(np.float32)
+    m = ref.OraclePoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, movement_variance=mv, dtype=np.float32,
+                                     tuning_basis=basis, params=params)
+    y = d["y"].astype(np.float32)
+    _, logP, _, logM = m._transitions({})
+    with np.errstate(over="ignore"):
+        lp, _ = m.init_latent_posterior(sample_T, seed)
+    opt = ref.adam_init(m.params)
+    W = m.params
+    t_m, t_e = [], []
+    for it in range(n_warm + n_steps):
+        t0 = time.perf_counter()
+        yw, tw = ref.get_statistics(lp, y)
+        t1 = time.perf_counter()
+        res = ref.adam_run(W, opt, 1.0, basis, yw, tw, step_size=0.01, maxiter=1000, tol=1e-6)
+        W, opt = res["params"], res["opt_state"]
+        tuning = ref.get_tuning_softplus(W, basis)
+        t2 = time.perf_counter()
+        out = ref.smooth_all_step_combined_ma_chunk(y, tuning, logP, logM, m.ma_neuron_default, m.ma_latent_default,
+                                                    1.0, 10000, accumulate=True)
+        lp = ref.lse(out[0], axis=1)
+        t3 = time.perf_counter()
+        if it >= n_warm:
+            t_m.append(t2 - t1)
+            t_e.append((t1 - t0) + (t3 - t2))
+    tm, te = float(np.mean(t_m)), float(np.mean(t_e))
+    sec_full = tm + te * (full_T / sample_T)
+    return full_T / sec_full, {"t_mstep_s": tm, "t_estep_sample_s": te, "sample_bins": sample_T,
+                               "sec_per_iter_extrapolated": sec_full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, K, T, ls, mv = WORKLOADS[args.workload]
+    sample_T = args.cpu_sample_bins
+    rate, parts = cpu_reference_rate(N, K, ls, mv, sample_T, args.steps, args.warmup, T)
+    sec = parts["t_mstep_s"] + parts["t_estep_sample_s"]
+    sample = ("%d-bin sample of the workload per step (one EM iteration: default Adam M-step %.2f s, T-independent; "
+              "statistics + chunked log-space filter/smoother with the [2,2,K,K] joint accumulation %.2f s, linear "
+              "in T); value = T/(t_mstep + T/%d * t_estep) extrapolated to T=%d"
+              % (sample_T, parts["t_mstep_s"], parts["t_estep_sample_s"], sample_T, T))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: N=%d K=%d T=%d (CPU arm timed on %d bins/step)" % (args.workload, N, K, T, sample_T)},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": sample + "; restated reference (NumPy CPU), not JAX: jax/optax are not "
+                                                "installable here; BLAS may use %d threads for the GEMMs" % (os.cpu_count() or 1)},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------------
+class PhaseTimer:
+    """CUDA events between the phases of an EM iteration (all on the launching stream)."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.marks = []
+        self.enabled = False
+
+    def hook(self, name):
+        if not self.enabled:
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.marks.append((name, ev))
+
+    def summarize(self):
+        tot = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            if n1 == "begin":
+                continue
+            tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+        return tot
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import poor_man_gplvm_b200 as pmg
+    from poor_man_gplvm_b200 import ops
+    from poor_man_gplvm_b200.core import EMLoop
+    from poor_man_gplvm_b200.synthetic import make_dataset_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, K, T, ls, mv = WORKLOADS[args.workload]
+    if args.bins:
+        T = args.bins
+    # weak scaling: every rank owns T bins of the same synthetic process (independent time blocks)
+    data = make_dataset_torch(T, N, K, dev, seed=1234 + rank)
+    y_dev = data["y"].to(torch.float32).contiguous()
+    model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, movement_variance=mv, device=dev)
+    rng = np.random.default_rng(1)
+    model.params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
+    P, logP, M, logM, op = model._transition_pack({})
+    ma_n, ma_l = model._masks(None, None, T)
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    post0 = torch.rand((T, K), generator=g, device=dev)
+    lp0 = torch.log(post0 / post0.sum(dim=1, keepdim=True))
+    del post0
+    loop = EMLoop(model, y_dev, op, ma_n, ma_l, 1.0, model.tuning_basis, lp0, model.param_prior_std,
+                  0.01, args.m_step_maxiter, args.m_step_tol)
+    del lp0
+
+    timer = PhaseTimer(torch)
+    ops.PHASE_HOOK = timer.hook
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loop.iteration()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    timer.enabled = True
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    relays = 0
+    n_adam = []
+    for _ in range(args.steps):
+        timer.hook("begin")
+        res, m_res = loop.iteration()
+        relays += res.n_relay_fwd + res.n_relay_bwd
+        n_adam.append(m_res[2])
+    ev1.record()
+    barrier()
+    timer.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = ops.LAUNCHES - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    phases = timer.summarize()
+    n_adam = [int(x.item()) for x in n_adam]
+    ops.PHASE_HOOK = None
+    value = world * T * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes / flops per launch)
+    pk = peaks()
+    S = args.steps
+    per = {k: v / S for k, v in phases.items()}     # ms per EM iteration per phase
+    algo = {
+        "forward": ("hbm", 12.0 * K * T),           # read ll 4K, write alpha 8K   bytes per bin
+        "backward": ("hbm", 16.0 * K * T),          # read ll 4K + alpha 8K, write gamma_lat 4K
+        "emission": ("tensor", 2.0 * T * N * K),
+        "stats": ("tensor", 2.0 * T * N * K),
+    }
+    roof_all = {}
+    for name, (bound, amount) in algo.items():
+        if name not in per or per[name] <= 0:
+            continue
+        sec = per[name] * 1e-3
+        if bound == "hbm":
+            ach, peak, unit = amount / sec / 1e9, pk["hbm_gbs"], "GB/s"
+        else:
+            # fp32-equivalent GEMM flops against the derived TF32 dense peak = measured bf16 / 2
+            ach, peak, unit = amount / sec / 1e12, pk["bf16_tflops_sustained"] / 2.0, "TFLOP/s"
+        roof_all[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                          "ms": per[name]}
+    dominant = max((k for k in roof_all), key=lambda k: roof_all[k]["ms"]) if roof_all else None
+    roofline = None
+    if dominant:
+        r = dict(roof_all[dominant])
+        r.update({"kernel": dominant, "traffic": None, "peak_source": pk["src"]})
+        roofline = r
+
+    # ---- end-to-end through the public API with host buffers (rank-local block; same n_iter per rank)
+    e2e = None
+    if not args.no_e2e:
+        n_iter = args.e2e_iters
+        y_host = y_dev.cpu().numpy()
+        lp_host, _ = model.init_latent_posterior(T, key=5)
+        barrier()
+        t0 = time.perf_counter()
+        em = model.fit_em(y_host, n_iter=n_iter, log_posterior_init=lp_host, m_step_maxiter=args.m_step_maxiter,
+                          m_step_tol=args.m_step_tol)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+        d2h = sum(int(np.asarray(v).nbytes) for k, v in em.items()
+                  if isinstance(v, np.ndarray)) + sum(int(a.nbytes) for a in em["log_posterior_all_saved"])
+        e2e = {"value": world * T * n_iter / wall, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes / n_iter),
+               "d2h_bytes_per_step": int(d2h / n_iter), "n_iter": n_iter, "wall_s": wall,
+               "note": "fit_em(y_host,...) incl. H2D of y and D2H of every em_res array; bytes are per EM iteration"}
+        del em, y_host
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, parts = cpu_reference_rate(N, K, ls, mv, args.cpu_sample_bins, 1, 0, T)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": "1 EM iteration on a %d-bin sample of the workload (M-step %.1f s, statistics+E-step "
+                                  "%.1f s), extrapolated linearly in T to T=%d; restated reference (NumPy CPU, fp32, "
+                                  "reference operation order), not JAX"
+                                  % (args.cpu_sample_bins, parts["t_mstep_s"], parts["t_estep_sample_s"], T)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s: N=%d K=%d T=%d bins per GPU, tuning_lengthscale=%g (B=%d), "
+                                       "movement_variance=%g, Adam maxiter=%d tol=%g"
+                                       % (args.workload, N, K, T, ls, model.n_basis, mv, args.m_step_maxiter,
+                                          args.m_step_tol),
+                           "l2": "inputs larger than L2 (y, ll, alpha, gamma each >= 1 GB at the headline size)",
+                           "n_chain": loop.es.plan.n_chain, "chunk_len": loop.es.chunk_len, "halo": loop.es.halo,
+                           "seam_relays_in_timed_region": relays, "adam_steps_per_iter": n_adam},
+                "phases_ms_per_step": per, "roofline": roofline, "roofline_all": roof_all,
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--bins", type=int, default=0, help="override T (bins per GPU)")
+    ap.add_argument("--m-step-maxiter", type=int, default=1000)
+    ap.add_argument("--m-step-tol", type=float, default=1e-6)
+    ap.add_argument("--e2e-iters", type=int, default=20)
+    ap.add_argument("--cpu-sample-bins", type=int, default=200)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+/*
+ * pmgplvm_b200 — C ABI of the B200-native EM hot path of PoissonGPLVMJump1D.
+ *
+ * One shared library (libpmgplvm_b200.so), plain pointers and sizes only.  All
+ * array pointers are DEVICE pointers owned by the caller (PyTorch allocates
+ * them), row-major fp32 unless stated, with explicit leading dimensions in
+ * elements.  Every entry point enqueues work on `stream` and returns without a
+ * host synchronisation.  Return value: 0 = ok, negative = bad argument
+ * (PMG_ERR_*), positive = cudaError_t of a failed runtime call.
+ *
+ * Each function cites the reference (poor_man_gplvm/...) code it replaces;
+ * "SURVEY" ids (E1..D3) are the rows of SURVEY.md section 8(a).
+ */
+#ifndef PMGPLVM_B200_H
+#define PMGPLVM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pmg_stream_t; /* cudaStream_t */
+
+#define PMG_OK 0
+#define PMG_ERR_BAD_ARG (-1)
+#define PMG_ERR_UNSUPPORTED_SHAPE (-2)
+#define PMG_ERR_ALIGNMENT (-3)
+#define PMG_ERR_WORKSPACE (-4)
+
+int pmg_version(void);
+const char* pmg_error_string(int code);
+/* number of SMs of the current device (grid sizing on the host side) */
+int pmg_sm_count(void);
+
+/* ------------------------------------------------------------------ E1/E2 --
+ * Poisson emission log-likelihood, decoder.py:30-48 vmapped by :60-85, in
+ * GEMM form:  ll[t,k] = sum_n y[t,n]*loglam[k,n] - lam_sum[k] - lgam[t],
+ * ll[t,k] = -1e20 where ma_latent[k] == 0.
+ */
+
+/* loglam[k,n] = ma_neuron[n]*log(tuning[k,n]*dt + 1e-20);
+ * lam_sum[k]  = sum_n ma_neuron[n]*(tuning[k,n]*dt + 1e-20).  ma_neuron may be NULL (= ones). */
+int pmg_emission_prepare(int K, int N, const float* tuning, const float* ma_neuron, float dt,
+                         float* loglam, float* lam_sum, pmg_stream_t stream);
+
+/* lgam[t] = sum_n ma_neuron[n]*lgamma(y[t,n]+1)   (y-only term; constant across EM iterations) */
+int pmg_emission_lgamma_rowsum(int64_t T, int N, const float* y, int64_t ldy,
+                               const float* ma_neuron, float* lgam, pmg_stream_t stream);
+
+/* impl: 0 = default (tcgen05 when the shape allows it), 1 = CUDA-core fp32 tiles (cross-check). */
+int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,
+                         const float* lam_sum, const float* lgam, const float* ma_latent,
+                         float* ll, int64_t ldll, int impl, pmg_stream_t stream);
+
+/* -------------------------------------------------------------------- E3 --
+ * Naive-Bayes normalisation, decoder.py:88-102: lml_t = logsumexp_k ll[t,:],
+ * log_post = ll - lml_t.  log_post may alias ll.
+ */
+int pmg_naive_bayes_normalize(int64_t T, int K, const float* ll, int64_t ldll, float* log_post,
+                              int64_t ldp, float* lml_t, pmg_stream_t stream);
+
+/* ------------------------------------------------------------- F1/F2, S1-S3 --
+ * Forward filter (decoder.py:151-198) and backward smoother (decoder.py:200-332)
+ * in linear space, parallel in time over `n_chain`
+ * contiguous chunks of `chunk_len` bins; a chain warms up over `halo` bins
+ * from the uniform carry and records its warmed-up state so that
+ * pmg_seam_check can verify it against the neighbouring chain's true state.
+ */
+typedef struct pmg_transition {
+  int K;              /* latent bins */
+  int kind;           /* 0 = Toeplitz RBF: P0[x,x'] = taps[|x-x'|]*inv_z[x];  1 = banded/dense general */
+  int W;              /* band half width: P0[x,x'] == 0 for |x-x'| > W */
+  const float* taps;  /* kind 0: [W+1] */
+  const float* inv_z; /* kind 0: [K] */
+  const float* band_fwd; /* kind 1: [2W+1, K]: band_fwd[j,x'] = P0[x'-W+j, x'] (0 outside) */
+  const float* band_bwd; /* kind 1: [2W+1, K]: band_bwd[j,x ] = P0[x, x-W+j]  (0 outside) */
+  float M[4];         /* dynamics transition M[d,d'] row-major, (from, to) */
+} pmg_transition;
+
+typedef struct pmg_scan_plan {
+  int64_t T;          /* bins held locally (including any halo bins fetched from neighbours) */
+  int64_t core_begin; /* outputs are produced for bins [core_begin, core_end) */
+  int64_t core_end;
+  int64_t chunk_len;  /* bins per chain */
+  int n_chain;        /* ceil((core_end-core_begin)/chunk_len) */
+  int halo;           /* warm-up bins */
+  int left_exact;     /* bin 0 is the true start of the sequence (or carry_in is exact) */
+  int right_exact;    /* bin T-1 is the true end of the sequence (or beta_in is exact) */
+  float likelihood_scale;
+} pmg_scan_plan;
+
+/* mode 0: all chains, warm-up from the uniform carry (left-most chain exact if left_exact).
+ * mode 1: relay — run only chains listed in chain_ids[n_ids] (device int32) starting
+ *         from the exact carry alpha[t_begin-1].
+ * alpha:   [T, 2, K] (ld = 2*ldk), lmr: [T] = log c_t + s*max_k ll[t,k]
+ * carry_in: [2,K] or NULL (uniform);   halo_state: [n_chain, 2, K] warmed-up state at t_begin-1. */
+int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                const float* carry_in, float* alpha, float* lmr, float* halo_state, int mode,
+                const int* chain_ids, int n_ids, pmg_stream_t stream);
+
+/* gamma:      [T, 2, K] or NULL; gamma_lat: [T, K] or NULL (sum over dynamics); dyn_marg: [T,2] or NULL
+ * r_out:      [T, 2, K] or NULL (r[t] = L_t*beta_t/c_t, the right factor of the transition counts)
+ * tw_partial: [n_chain, K] or NULL (per-chain sum_t gamma_lat)
+ * beta_in:    [2,K] or NULL (ones);  beta_halo / beta_end: [n_chain, 2, K]. */
+int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                 const float* alpha, const float* beta_in, float* gamma, float* gamma_lat,
+                 float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo, float* beta_end,
+                 int mode, const int* chain_ids, int n_ids, pmg_stream_t stream);
+
+/* err[i] = max relative difference between est[i,:] and truth[i,:] over entries > floor.
+ * est/truth are [n, len] with row strides in elements (truth rows may live inside alpha). */
+int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, const float* truth,
+                   int64_t ld_truth, float floor_val, float* err, pmg_stream_t stream);
+
+/* ------------------------------------------------------------------ M1, S4 --
+ * C[m,n] = sum_t A[t,m]*B[t,n]  (time is the reduction axis).  Used for the
+ * sufficient statistics (fit_tuning_helper.py:28-42: A = gamma_lat, B = y) and
+ * for the transition counts (decoder.py:215-221 via SURVEY S4: A = alpha, B = r).
+ * workspace: pmg_atb_workspace_bytes(...) bytes, or NULL when that returns 0.
+ */
+int64_t pmg_atb_workspace_bytes(int64_t T, int M, int N, int impl);
+int pmg_atb(int64_t T, int M, int N, const float* A, int64_t lda, const float* B, int64_t ldb,
+            float* C, int64_t ldc, void* workspace, int64_t workspace_bytes, int impl,
+            pmg_stream_t stream);
+
+/* log_acc[d,d',x,x'] = logM[d,d'] + logP_{d'}[x,x'] + log G[(d,x),(d',x')]   (G = alpha^T r, [2K,2K]):
+ * decoder.py:221's accumulator; using the analytic log kernel keeps deep tails finite.
+ * logP: device [2,K,K]; logM: HOST float[4] row-major (from, to). */
+int pmg_xi_finalize(int K, const float* G, const float* logP, const float* logM,
+                    float* log_acc /*[2,2,K,K]*/, pmg_stream_t stream);
+
+/* -------------------------------------------------------------------- M2/M3 --
+ * Adam M-step, fit_tuning_helper.py:124-196 on the objective :63-81 with the
+ * softplus link :19-25.  One cooperative persistent kernel; CTA per neuron tile.
+ * W, mu, nu: [B,N] in/out; count: device int32 in/out (optax count);
+ * loss_hist/err_hist: [maxiter] out (zero beyond n_iter); n_iter_out: device int32;
+ * final: device float[2] = (final_loss, final_error); tuning_out: [K,N] = softplus(Phi W_final).
+ * workspace: pmg_mstep_workspace_bytes(...) bytes, zero-initialised by the callee.
+ */
+int64_t pmg_mstep_workspace_bytes(int K, int B, int N, int maxiter);
+int pmg_mstep_adam(int K, int B, int N, const float* Phi, const float* yw, const float* tw,
+                   float prior_std, float lr, float b1, float b2, float eps, int maxiter, float tol,
+                   int min_iters, float* W, float* mu, float* nu, int* count, float* loss_hist,
+                   float* err_hist, int* n_iter_out, float* final_out, float* tuning_out,
+                   void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
+
+/* tuning[k,n] = softplus(sum_b Phi[k,b]*W[b,n])   (fit_tuning_helper.py:11-25) */
+int pmg_tuning_softplus(int K, int B, int N, const float* Phi, const float* W, float* tuning,
+                        pmg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMGPLVM_B200_H */

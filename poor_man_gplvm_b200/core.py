@@ -1,0 +1,456 @@
+"""PoissonGPLVMJump1D — drop-in for the reference class of the same name.
+
+Host logic of reference ``poor_man_gplvm/core.py``: ``AbstractGPLVMJump1D``
+(:376-733) and ``PoissonGPLVMJump1D`` (:746-849).  Same constructor, method
+names, keyword arguments and result-dictionary keys; the numerics run in the
+hand-written sm_100a kernels behind ``libpmgplvm_b200.so`` (no JAX, no CPU
+fallback).  Arrays come back as NumPy arrays (pass ``return_device=True`` to
+``fit_em`` / ``decode_latent*`` to keep T-sized results on the GPU as torch
+tensors and skip the device->host copies).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import gp_kernel as gpk
+from . import ops
+from .estep import EStep
+
+
+def _unwrap_tsd(y):
+    """pynapple TsdFrame duck-typing (reference core.py:459-461): returns (values, times or None)."""
+    if hasattr(y, "d") and hasattr(y, "t") and not isinstance(y, (np.ndarray, torch.Tensor)):
+        return y.d, y.t
+    return y, None
+
+
+def _rewrap_tsd(arr, t_l):
+    if t_l is None:
+        return arr
+    try:
+        import pynapple as nap   # optional; only when the caller handed us a TsdFrame
+        return nap.TsdFrame(d=arr, t=t_l)
+    except Exception:
+        return arr
+
+
+def _seed_from_key(key):
+    if key is None:
+        return 0
+    a = np.asarray(key).astype(np.uint64).ravel()
+    return int(a[-1]) if a.size else 0
+
+
+def compute_transition_posterior_prob(log_acc):
+    """reference decoder.py:334-375 on a torch tensor [2,2,K,K] -> dict of 12 tensors."""
+    lse = torch.logsumexp
+    log_joint_full = log_acc - lse(log_acc.reshape(-1), 0)
+    log_joint_latent = lse(log_joint_full, dim=(0, 1))
+    log_joint_dynamics = lse(log_joint_full, dim=(2, 3))
+    log_transition_latent = log_joint_latent - lse(log_joint_latent, dim=1, keepdim=True)
+    log_transition_dynamics = log_joint_dynamics - lse(log_joint_dynamics, dim=1, keepdim=True)
+    log_transition_full = log_joint_full - lse(log_joint_full, dim=(1, 3), keepdim=True)
+    res = {'p_joint_full': torch.exp(log_joint_full),
+           'p_joint_latent': torch.exp(log_joint_latent),
+           'p_joint_dynamics': torch.exp(log_joint_dynamics),
+           'p_transition_full': torch.exp(log_transition_full),
+           'p_transition_latent': torch.exp(log_transition_latent),
+           'p_transition_dynamics': torch.exp(log_transition_dynamics),
+           'log_joint_full': log_joint_full,
+           'log_joint_latent': log_joint_latent,
+           'log_joint_dynamics': log_joint_dynamics,
+           'log_transition_full': log_transition_full,
+           'log_transition_latent': log_transition_latent,
+           'log_transition_dynamics': log_transition_dynamics}
+    return res
+
+
+class EMLoop:
+    """Device-resident state of one EM run (reference core.py:640-676): the posterior over latent bins,
+    the GLM weights with their Adam state, and the E-step buffers.  ``iteration`` is the loop body of
+    ``fit_em``: statistics -> Adam M-step -> tuning -> E-step."""
+
+    def __init__(self, model, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
+                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None):
+        self.y = y_dev
+        self.Phi = model._dev(tuning_basis)
+        self.W = model._dev(model.params).clone()
+        if self.W.shape != (self.Phi.shape[1], model.n_neuron):
+            raise ValueError("params shape %s does not match basis %s" % (tuple(self.W.shape), tuple(self.Phi.shape)))
+        self.state = ops.AdamState(self.W)
+        self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len)
+        self.gamma_lat = torch.exp(model._dev(log_posterior_init))
+        if self.gamma_lat.shape != (y_dev.shape[0], op.K):
+            raise ValueError("log_posterior_init must be [T, n_latent_bin]")
+        self.tw = self.gamma_lat.sum(dim=0, dtype=torch.float64).to(torch.float32)
+        self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
+
+    def iteration(self, want_gamma=False, want_dyn=False):
+        yw = ops.atb(self.gamma_lat, self.y)                       # reference core.py:807
+        ops.phase("stats")
+        m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
+                               self.maxiter, self.tol)             # reference core.py:810
+        ops.phase("mstep")
+        res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=True, want_dyn=want_dyn, want_r=False)
+        self.gamma_lat, self.tw = res.gamma_lat, res.tw            # reference core.py:668
+        return res, m_res
+
+
+class PoissonGPLVMJump1D:
+    """Poisson GPLVM with a smooth 1-D latent plus jumps (reference core.py:746)."""
+
+    def __init__(self, n_neuron, n_latent_bin=100, tuning_lengthscale=1., param_prior_std=1.,
+                 movement_variance=1.,
+                 explained_variance_threshold_basis=0.999,
+                 rng_init_int=123,
+                 w_init_variance=1.,
+                 w_init_mean=0.,
+                 p_move_to_jump=0.01,
+                 p_jump_to_move=0.01,
+                 basis_type='rbf',
+                 custom_tuning_kernel=None,
+                 custom_transition_kernel=None,
+                 smoothness_penalty=0.,
+                 device=None):
+        if basis_type not in ('rbf', 'custom_kernel'):
+            raise ValueError("basis_type %r is not supported (the reference disables bspline too, core.py:57-59)"
+                             % (basis_type,))
+        self.n_latent_bin = n_latent_bin
+        self.tuning_lengthscale = tuning_lengthscale
+        self.param_prior_std = param_prior_std
+        self.movement_variance = movement_variance
+        self.p_move_to_jump = p_move_to_jump
+        self.p_jump_to_move = p_jump_to_move
+        self.explained_variance_threshold_basis = explained_variance_threshold_basis
+        self.rng_init_int = rng_init_int
+        self.rng_init = rng_init_int
+        self.n_neuron = n_neuron
+        self.possible_latent_bin = np.arange(n_latent_bin)
+        self.possible_dynamics = np.arange(2)
+        self.w_init_variance = w_init_variance
+        self.w_init_mean = w_init_mean
+        self.custom_transition_kernel = custom_transition_kernel
+        self.basis_type = basis_type
+        self.tuning_basis = gpk.generate_basis(tuning_lengthscale, n_latent_bin, explained_variance_threshold_basis,
+                                               include_bias=True, basis_type=basis_type,
+                                               custom_kernel=custom_tuning_kernel)
+        self.n_basis = self.tuning_basis.shape[1]
+        self.smoothness_penalty = smoothness_penalty
+        self.ma_neuron_default = np.ones(n_neuron, dtype=np.float32)
+        self.ma_latent_default = np.ones(n_latent_bin, dtype=np.float32)
+        self._device = device
+        self.adam_runner = None
+        self.opt_state_init_fun = None
+        self.initialize_params(self.rng_init)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def device(self):
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("poor_man_gplvm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self._device)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['adam_runner'] = None
+        state['opt_state_init_fun'] = None
+        state.pop('_opt_state', None)          # device tensors; fit_em re-initialises Adam anyway (core.py:847)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    def _dev(self, a, dtype=torch.float32):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(a)), device=self.device).to(dtype).contiguous()
+
+    @staticmethod
+    def _host(t):
+        return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+    # ------------------------------------------------------------------ reference API
+    def get_tuning(self, params, hyperparam, tuning_basis):
+        """softplus(basis @ params)  (reference core.py:772-774).  NumPy in -> NumPy out."""
+        Phi, W = self._dev(tuning_basis), self._dev(params)
+        return self._host(ops.tuning_softplus(Phi, W))
+
+    def initialize_params(self, key):
+        """reference core.py:429-437.  NOTE: NumPy PRNG, not JAX threefry: set
+        ``model.params`` explicitly for key-for-key reproduction of a reference run."""
+        rng = np.random.default_rng(_seed_from_key(key))
+        params = (rng.standard_normal((self.n_basis, self.n_neuron)) * np.sqrt(self.w_init_variance)
+                  + self.w_init_mean).astype(np.float32)
+        self.params = params
+        # softplus(Phi W) on the host: the constructor must work without touching the GPU
+        self.tuning = np.logaddexp(self.tuning_basis @ params, np.float32(0)).astype(np.float32)
+        return self.params, self.tuning
+
+    def init_latent_posterior(self, T, key, random_scale=0.1):
+        """reference core.py:571-583 (NumPy PRNG stream)."""
+        rng = np.random.default_rng(_seed_from_key(key))
+        posterior = (rng.random((T, self.n_latent_bin), dtype=np.float32) * np.float32(random_scale))
+        posterior = posterior / posterior.sum(axis=1, keepdims=True)
+        with np.errstate(divide="ignore"):
+            log_posterior = np.log(posterior)
+        log_posterior = np.where(np.isneginf(log_posterior), np.float32(-np.inf), log_posterior)
+        return log_posterior, posterior
+
+    def _transition_pack(self, hyperparam):
+        mv = hyperparam.get('movement_variance', self.movement_variance)
+        pmj = hyperparam.get('p_move_to_jump', self.p_move_to_jump)
+        pjm = hyperparam.get('p_jump_to_move', self.p_jump_to_move)
+        P, logP, M, logM = gpk.create_transition_prob_1d(self.possible_latent_bin, self.possible_dynamics, mv, pmj, pjm,
+                                                         custom_kernel=self.custom_transition_kernel)
+        host = gpk.move_operator_host(self.n_latent_bin, mv, self.custom_transition_kernel)
+        op = ops.MoveOperator(host, M, self.device)
+        return P, logP, M, logM, op
+
+    def _masks(self, ma_neuron, ma_latent, T):
+        if ma_neuron is None:
+            ma_neuron = self.ma_neuron_default
+        if ma_latent is None:
+            ma_latent = self.ma_latent_default
+        ma_n = np.asarray(self._host(ma_neuron), dtype=np.float32)
+        if ma_n.ndim == 2:
+            raise NotImplementedError("spatio-temporal ma_neuron [T,N] is not on the CUDA path yet (SURVEY F4)")
+        ma_l = np.asarray(self._host(ma_latent), dtype=np.float32)
+        return self._dev(ma_n), self._dev(ma_l)
+
+    def _decode_latent(self, y, tuning, hyperparam, log_latent_transition_kernel_l=None,
+                       log_dynamics_transition_kernel=None, ma_neuron=None, ma_latent=None, likelihood_scale=1.,
+                       n_time_per_chunk=10000, return_device=False, _want_r=True):
+        """reference core.py:777-786: returns the 6-tuple (log_acausal_posterior_all [T,2,K],
+        log_marginal_final, log_causal_posterior_all [T,2,K], log_one_step_predictive_marginals [T],
+        log_accumulated_joint_total [2,2,K,K], log_likelihood_all [T,K]).  The transition kernels are
+        rebuilt from ``hyperparam``/attributes (the log arguments are accepted for signature
+        compatibility); ``n_time_per_chunk`` is a numerical no-op in the reference and ignored here."""
+        y, _ = _unwrap_tsd(y)
+        y_dev = self._dev(y)
+        P, logP, M, logM, op = self._transition_pack(hyperparam)
+        ma_n, ma_l = self._masks(ma_neuron, ma_latent, y_dev.shape[0])
+        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale)
+        res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=False, want_dyn=False, want_r=_want_r)
+        log_acc = None
+        if _want_r and y_dev.shape[0] > 1:
+            T, K = y_dev.shape[0], self.n_latent_bin
+            G = ops.atb(res.alpha.view(T, 2 * K)[:T - 1], res.r.view(T, 2 * K)[1:])
+            log_acc = ops.xi_finalize(G, self._dev(logP), logM)
+        out = (torch.log(res.gamma), res.log_marginal.to(torch.float32), torch.log(res.alpha), res.lmr, log_acc,
+               res.ll)
+        if return_device:
+            return out
+        return tuple(None if o is None else self._host(o) for o in out)
+
+    def decode_latent(self, y, tuning=None, hyperparam={}, ma_neuron=None, ma_latent=None, likelihood_scale=1.,
+                      n_time_per_chunk=10000, t_l=None, return_device=False):
+        """reference core.py:454-497 (same keys)."""
+        y, t_in = _unwrap_tsd(y)
+        if t_in is not None:
+            t_l = t_in
+        if tuning is None:
+            tuning = self.tuning
+        y_dev = self._dev(y)
+        T, K = y_dev.shape[0], self.n_latent_bin
+        P, logP, M, logM, op = self._transition_pack(hyperparam)
+        ma_n, ma_l = self._masks(ma_neuron, ma_latent, T)
+        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale)
+        res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=True, want_dyn=True, want_r=T > 1)
+        conv = (lambda t: t) if return_device else self._host
+        decoding_res = {'log_posterior_all': conv(torch.log(res.gamma)),
+                        'log_marginal_final': float(res.log_marginal.item()),
+                        'posterior_all': conv(res.gamma),
+                        'posterior_latent_marg': _rewrap_tsd(conv(res.gamma_lat), t_l),
+                        'posterior_dynamics_marg': _rewrap_tsd(conv(res.dyn_marg), t_l),
+                        'log_one_step_predictive_marginals_all': conv(res.lmr),
+                        'log_likelihood_all': conv(res.ll)}
+        if T > 1:
+            G = ops.atb(res.alpha.view(T, 2 * K)[:T - 1], res.r.view(T, 2 * K)[1:])
+            log_acc = ops.xi_finalize(G, self._dev(logP), logM)
+            tp = compute_transition_posterior_prob(log_acc)
+            decoding_res.update({k: conv(v) for k, v in tp.items()})
+        self._last_estep_info = {"n_chain": res.plan.n_chain, "relay_fwd": res.n_relay_fwd,
+                                 "relay_bwd": res.n_relay_bwd, "seam_err_fwd": res.seam_err_fwd,
+                                 "seam_err_bwd": res.seam_err_bwd}
+        return decoding_res
+
+    def decode_latent_naive_bayes(self, y, tuning=None, hyperparam={}, ma_neuron=None, ma_latent=None,
+                                  likelihood_scale=1., n_time_per_chunk=10000, dt_l=1., t_l=None,
+                                  return_device=False):
+        """reference core.py:788-792 -> :499-524 (``likelihood_scale`` accepted and ignored, as there)."""
+        y, t_in = _unwrap_tsd(y)
+        if t_in is not None:
+            t_l = t_in
+        if tuning is None:
+            tuning = self.tuning
+        y_dev = self._dev(y)
+        T = y_dev.shape[0]
+        ma_n, ma_l = self._masks(ma_neuron, ma_latent, T)
+        dt_arr = np.asarray(self._host(dt_l), dtype=np.float32)
+        if dt_arr.ndim > 0 and dt_arr.size > 1 and not np.all(dt_arr == dt_arr.flat[0]):
+            raise NotImplementedError("per-bin dt_l is not on the CUDA path yet (SURVEY F4)")
+        dt = float(dt_arr.flat[0]) if dt_arr.size else 1.0
+        loglam, lam_sum = ops.emission_prepare(self._dev(tuning), ma_n, dt)
+        lgam = ops.lgamma_rowsum(y_dev, ma_n)
+        ll = ops.emission_poisson(y_dev, loglam, lam_sum, lgam, ma_l)
+        log_post, lml = ops.naive_bayes_normalize(ll)
+        conv = (lambda t: t) if return_device else self._host
+        return {'log_posterior_latent': conv(log_post),
+                'log_marginal_l': conv(lml),
+                'log_marginal_total': float(lml.sum(dtype=torch.float64).item()),
+                'posterior_latent': _rewrap_tsd(conv(torch.exp(log_post)), t_l),
+                'll_per_pos_l': conv(ll)}
+
+    def m_step(self, param_curr, y, log_posterior_curr, tuning_basis, hyperparam, opt_state_curr=None,
+               m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6):
+        """reference core.py:802-827: sufficient statistics + Adam loop.  NumPy/torch in, dict out."""
+        y_dev = self._dev(_unwrap_tsd(y)[0])
+        post = torch.exp(self._dev(log_posterior_curr))
+        yw = ops.atb(post, y_dev)
+        tw = post.sum(dim=0, dtype=torch.float64).to(torch.float32)
+        W = self._dev(param_curr).clone()
+        state = opt_state_curr if isinstance(opt_state_curr, ops.AdamState) else ops.AdamState(W)
+        prior_std = hyperparam.get('param_prior_std', self.param_prior_std)
+        lh, eh, n_it, fin, tuning = ops.mstep_adam(self._dev(tuning_basis), yw, tw, W, state, prior_std,
+                                                   m_step_step_size, m_step_maxiter, m_step_tol)
+        n = int(n_it.item())
+        return {'params': self._host(W), 'opt_state': state, 'n_iter': n,
+                'final_loss': float(fin[0].item()), 'final_error': float(fin[1].item()),
+                'loss_history': self._host(lh[:n]), 'error_history': self._host(eh[:n])}
+
+    def fit_em(self, y, hyperparam={}, key=0,
+               n_iter=20, log_posterior_init=None, ma_neuron=None, ma_latent=None,
+               n_time_per_chunk=10000, dt=1., likelihood_scale=1.,
+               save_every=None,
+               m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6,
+               posterior_init_kwargs={'random_scale': 0.1}, verboase=True, return_device=False,
+               **kwargs):
+        """reference core.py:829-849 -> :592-713.  Per iteration: M-step (statistics + Adam) on the
+        current posterior, tuning, E-step; ``em_res`` has the reference's keys."""
+        y_in, t_l = _unwrap_tsd(y)
+        hyperparam_ = dict(hyperparam)
+        prior_std = hyperparam_.get('param_prior_std', self.param_prior_std)
+        hyperparam_['param_prior_std'] = prior_std
+        hyperparam_['smoothness_penalty'] = hyperparam_.get('smoothness_penalty', self.smoothness_penalty)
+
+        self.tuning_lengthscale = hyperparam_.get('tuning_lengthscale', self.tuning_lengthscale)
+        self.movement_variance = hyperparam_.get('movement_variance', self.movement_variance)
+        self.p_move_to_jump = hyperparam_.get('p_move_to_jump', self.p_move_to_jump)
+        self.p_jump_to_move = hyperparam_.get('p_jump_to_move', self.p_jump_to_move)
+
+        y_dev = self._dev(y_in)                       # the one host->device copy of the spikes
+        T, K = y_dev.shape[0], self.n_latent_bin
+        if save_every is None:
+            save_every = n_iter
+        P, logP, M, logM, op = self._transition_pack(hyperparam_)
+        ma_n, ma_l = self._masks(ma_neuron, ma_latent, T)
+        if 'tuning_lengthscale' in hyperparam:
+            tuning_basis = gpk.generate_basis(self.tuning_lengthscale, K, self.explained_variance_threshold_basis,
+                                              include_bias=True)
+        else:
+            tuning_basis = self.tuning_basis
+        if log_posterior_init is None:
+            log_posterior_init, _ = self.init_latent_posterior(T, key, **posterior_init_kwargs)
+        loop = EMLoop(self, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
+                      m_step_step_size, m_step_maxiter, m_step_tol)
+        self.opt_state_init_fun = ops.AdamState
+        W, state, es = loop.W, loop.state, loop.es
+
+        lml_dev, m_hist = [], []
+        saved = {'log_posterior_all_saved': [], 'params_saved': [], 'tuning_saved': [], 'iter_saved': [],
+                 'log_marginal_saved': []}
+        estep_info = []
+        conv = (lambda t: t) if return_device else self._host
+        res = None
+        for i in range(n_iter):
+            last = i == n_iter - 1
+            snap = (i % save_every == 0)
+            res, m_res = loop.iteration(want_gamma=(last or snap), want_dyn=last)
+            m_hist.append(m_res)
+            tuning = m_res[4]
+            lml_dev.append(res.log_marginal)
+            estep_info.append((res.n_relay_fwd, res.n_relay_bwd, res.seam_err_fwd, res.seam_err_bwd))
+            if snap:
+                saved['log_posterior_all_saved'].append(conv(torch.log(res.gamma)))
+                saved['params_saved'].append(conv(W.clone()))
+                saved['tuning_saved'].append(conv(tuning))
+                saved['log_marginal_saved'].append(res.log_marginal)
+                saved['iter_saved'].append(i)
+
+        lml_host = torch.stack(lml_dev).cpu().numpy().astype(np.float32) if lml_dev else np.zeros(0, np.float32)
+        saved['log_marginal_saved'] = [np.float32(v.item()) for v in saved['log_marginal_saved']]
+        n_its = torch.cat([h[2] for h in m_hist]).cpu().numpy() if m_hist else np.zeros(0, np.int32)
+        m_step_res_l = {'n_iter': [int(n) for n in n_its],
+                        'final_loss': [float(h[3][0].item()) for h in m_hist],
+                        'final_error': [float(h[3][1].item()) for h in m_hist],
+                        'loss_history': [self._host(h[0][:int(n)]) for h, n in zip(m_hist, n_its)],
+                        'error_history': [self._host(h[1][:int(n)]) for h, n in zip(m_hist, n_its)]}
+
+        self.params = self._host(W)
+        self.tuning = self._host(tuning) if n_iter > 0 else self.tuning
+        self.log_marginal_final = lml_host[-1] if n_iter > 0 else None
+        self.log_latent_transition_kernel_l = logP
+        self.log_dynamics_transition_kernel = logM
+        self.tuning_basis = tuning_basis
+        self._last_estep_info = {"n_chain": es.plan.n_chain, "chunk_len": es.chunk_len, "halo": es.halo,
+                                 "per_iter": estep_info}
+        self._opt_state = state
+
+        em_res = dict(saved)
+        em_res.update({'log_posterior_init': log_posterior_init,
+                       'params': self.params,
+                       'tuning': self.tuning,
+                       'log_marginal_l': [v for v in lml_host],
+                       'm_step_res_l': m_step_res_l})
+        if n_iter > 0:
+            em_res.update({'log_posterior_final': conv(torch.log(res.gamma)),
+                           'log_marginal': lml_host[-1],
+                           'posterior': conv(res.gamma),
+                           'posterior_latent_marg': _rewrap_tsd(conv(res.gamma_lat), t_l),
+                           'posterior_dynamics_marg': _rewrap_tsd(conv(res.dyn_marg), t_l)})
+        return em_res
+
+    def predict_expected_rate(self, post_latent_marg, tuning=None):
+        """reference core.py:716-733: rate[t,n] = sum_p post[t,p] tuning[p,n]."""
+        if tuning is None:
+            tuning = self.tuning
+        vals, t_l = _unwrap_tsd(post_latent_marg)
+        rate = np.asarray(self._host(vals)) @ np.asarray(self._host(tuning))
+        return _rewrap_tsd(rate, t_l)
+
+    def sample_latent(self, T, key=0, movement_variance=1, p_move_to_jump=0.01, p_jump_to_move=0.01,
+                      init_dynamics=None, init_latent=None):
+        """reference core.py:526-555 (NumPy PRNG stream).  Returns [T,2] = (dynamics, latent)."""
+        rng = np.random.default_rng(_seed_from_key(key))
+        P, _, M, _ = gpk.create_transition_prob_1d(self.possible_latent_bin, self.possible_dynamics,
+                                                   movement_variance, p_move_to_jump, p_jump_to_move)
+        P = P.astype(np.float64); M = M.astype(np.float64)
+        P /= P.sum(axis=2, keepdims=True); M /= M.sum(axis=1, keepdims=True)
+        d = int(rng.integers(0, 2)) if init_dynamics is None else int(init_dynamics)
+        x = int(rng.integers(0, self.n_latent_bin)) if init_latent is None else int(init_latent)
+        out = np.empty((T, 2), dtype=np.int64)
+        for t in range(T):
+            d = int(rng.choice(2, p=M[d]))
+            x = int(rng.choice(self.n_latent_bin, p=P[d][x]))
+            out[t] = (d, x)
+        return out
+
+    def sample_y(self, latent_l, hyperparam={}, tuning=None, dt=1., key=10):
+        """reference core.py:794-800."""
+        if tuning is None:
+            tuning = self.tuning
+        rng = np.random.default_rng(_seed_from_key(key))
+        return rng.poisson(np.asarray(self._host(tuning))[np.asarray(latent_l)] * dt)
+
+    def sample(self, T, hyperparam={}, key=0, init_dynamics=None, init_latent=None, dt=1., tuning=None):
+        """reference core.py:558-569."""
+        mv = hyperparam.get('movement_variance', self.movement_variance)
+        pmj = hyperparam.get('p_move_to_jump', self.p_move_to_jump)
+        pjm = hyperparam.get('p_jump_to_move', self.p_jump_to_move)
+        seed = _seed_from_key(key)
+        latent_l = self.sample_latent(T, seed, mv, pmj, pjm, init_dynamics, init_latent)
+        y_l = self.sample_y(latent_l[:, 1], hyperparam, tuning, dt, seed + 1)
+        return latent_l, y_l

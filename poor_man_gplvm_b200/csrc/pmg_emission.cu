@@ -1,0 +1,186 @@
+// Poisson emission log-likelihood in GEMM form and the naive-Bayes normalisation.
+//
+// Replaces reference poor_man_gplvm/decoder.py:30-48 (get_loglikelihood_ma_poisson),
+// :60-85 (its vmap over time) and :88-102 (get_naive_bayes_ma):
+//   ll[t,k] = sum_n y[t,n] * (ma_n log lam[k,n]) - sum_n ma_n lam[k,n] - sum_n ma_n lgamma(y[t,n]+1)
+// with lam = tuning*dt + 1e-20 and ll = -1e20 on masked latent bins.
+#include "pmg_common.cuh"
+
+namespace pmg {
+
+// one CTA per latent bin k
+__global__ void emission_prepare_kernel(int K, int N, const float* __restrict__ tuning,
+                                        const float* __restrict__ ma_neuron, float dt,
+                                        float* __restrict__ loglam, float* __restrict__ lam_sum) {
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float m = ma_neuron ? ma_neuron[n] : 1.f;
+    const float lam = tuning[(size_t)k * N + n] * dt + kLamFloor;
+    loglam[(size_t)k * N + n] = m * logf(lam);
+    acc += (double)(m * lam);
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
+    lam_sum[k] = (float)s;
+  }
+}
+
+// one warp per time bin
+__global__ void lgamma_rowsum_kernel(int64_t T, int N, const float* __restrict__ y, int64_t ldy,
+                                     const float* __restrict__ ma_neuron, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int lane = threadIdx.x & 31;
+  const float* row = y + (size_t)t * ldy;
+  float acc = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float v = row[n];
+    // lgamma(1) = lgamma(2) = 0: skip the (dominant) 0/1 counts
+    const float lg = (v == 0.f || v == 1.f) ? 0.f : lgammaf(v + 1.f);
+    acc += (ma_neuron ? ma_neuron[n] : 1.f) * lg;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[t] = acc;
+}
+
+// ---- CUDA-core fp32 tile GEMM with the emission epilogue (cross-check path) ----
+constexpr int EM_BM = 128, EM_BN = 64, EM_BK = 16;
+
+__global__ void __launch_bounds__(256) emission_simt_kernel(int64_t T, int N, int K,
+                                                            const float* __restrict__ y, int64_t ldy,
+                                                            const float* __restrict__ loglam,
+                                                            const float* __restrict__ lam_sum,
+                                                            const float* __restrict__ lgam,
+                                                            const float* __restrict__ ma_latent,
+                                                            float* __restrict__ ll, int64_t ldll) {
+  __shared__ float As[EM_BK][EM_BM + 4];
+  __shared__ float Bs[EM_BK][EM_BN + 4];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int64_t t0 = (int64_t)blockIdx.x * EM_BM;
+  const int k0 = blockIdx.y * EM_BN;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int n0 = 0; n0 < N; n0 += EM_BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, cc = idx & 15;
+      const int64_t t = t0 + r;
+      const int n = n0 + cc;
+      As[cc][r] = (t < T && n < N) ? y[(size_t)t * ldy + n] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, cc = idx & 15;
+      const int k = k0 + r;
+      const int n = n0 + cc;
+      Bs[cc][r] = (k < K && n < N) ? loglam[(size_t)k * N + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < EM_BK; ++kk) {
+      float a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t t = t0 + ty * 8 + i;
+    if (t >= T) continue;
+    const float lg = lgam[t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= K) continue;
+      float v = acc[i][j] - lam_sum[k] - lg;
+      if (ma_latent && ma_latent[k] == 0.f) v = kVeryNegLL;
+      ll[(size_t)t * ldll + k] = v;
+    }
+  }
+}
+
+// one warp per time bin: lml = logsumexp_k ll, log_post = ll - lml
+__global__ void nb_normalize_kernel(int64_t T, int K, const float* __restrict__ ll, int64_t ldll,
+                                    float* __restrict__ log_post, int64_t ldp, float* __restrict__ lml_t) {
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int lane = threadIdx.x & 31;
+  const float* row = ll + (size_t)t * ldll;
+  float m = -INFINITY;
+  for (int k = lane; k < K; k += 32) m = fmaxf(m, row[k]);
+  m = warp_max(m);
+  if (!(fabsf(m) <= 3.0e38f)) m = 0.f;   // jax logsumexp: non-finite max -> 0
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += expf(row[k] - m);
+  s = warp_sum(s);
+  const float lml = logf(s) + m;
+  float* orow = log_post + (size_t)t * ldp;
+  for (int k = lane; k < K; k += 32) orow[k] = row[k] - lml;
+  if (lane == 0) lml_t[t] = lml;
+}
+
+}  // namespace pmg
+
+int pmg_emission_tc_launch(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,
+                           const float* lam_sum, const float* lgam, const float* ma_latent, float* ll,
+                           int64_t ldll, cudaStream_t st);   // pmg_gemm_tc.cu (returns PMG_ERR_UNSUPPORTED_SHAPE if n/a)
+
+extern "C" int pmg_emission_prepare(int K, int N, const float* tuning, const float* ma_neuron, float dt,
+                                    float* loglam, float* lam_sum, pmg_stream_t stream) {
+  if (K <= 0 || N <= 0 || !tuning || !loglam || !lam_sum) return PMG_ERR_BAD_ARG;
+  pmg::emission_prepare_kernel<<<K, 128, 0, (cudaStream_t)stream>>>(K, N, tuning, ma_neuron, dt, loglam, lam_sum);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_emission_lgamma_rowsum(int64_t T, int N, const float* y, int64_t ldy,
+                                          const float* ma_neuron, float* lgam, pmg_stream_t stream) {
+  if (T <= 0 || N <= 0 || !y || !lgam || ldy < N) return PMG_ERR_BAD_ARG;
+  pmg::lgamma_rowsum_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, N, y, ldy, ma_neuron, lgam);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,
+                                    const float* lam_sum, const float* lgam, const float* ma_latent, float* ll,
+                                    int64_t ldll, int impl, pmg_stream_t stream) {
+  if (T <= 0 || N <= 0 || K <= 0 || !y || !loglam || !lam_sum || !lgam || !ll) return PMG_ERR_BAD_ARG;
+  if (ldy < N || ldll < K) return PMG_ERR_BAD_ARG;
+  if (impl == 0) {
+    int rc = pmg_emission_tc_launch(T, N, K, y, ldy, loglam, lam_sum, lgam, ma_latent, ll, ldll, (cudaStream_t)stream);
+    if (rc != PMG_ERR_UNSUPPORTED_SHAPE) return rc;
+  }
+  dim3 grid(pmg::cdiv(T, pmg::EM_BM), pmg::cdiv(K, pmg::EM_BN));
+  pmg::emission_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, N, K, y, ldy, loglam, lam_sum, lgam,
+                                                                   ma_latent, ll, ldll);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_naive_bayes_normalize(int64_t T, int K, const float* ll, int64_t ldll, float* log_post,
+                                         int64_t ldp, float* lml_t, pmg_stream_t stream) {
+  if (T <= 0 || K <= 0 || !ll || !log_post || !lml_t || ldll < K || ldp < K) return PMG_ERR_BAD_ARG;
+  pmg::nb_normalize_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, K, ll, ldll, log_post, ldp, lml_t);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}

@@ -1,0 +1,265 @@
+"""Operator layer: PyTorch tensors in, C-ABI calls on the current CUDA stream.
+
+PyTorch is used only for device memory and streams.  Every function here
+launches the hand-written sm_100a kernels of libpmgplvm_b200.so; nothing falls
+back to torch ops or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PmgScanPlan, PmgTransition, check
+
+
+LAUNCHES = 0          # kernels of libpmgplvm_b200.so launched so far (bench.py reports the delta)
+PHASE_HOOK = None     # optional callable(name): bench.py records CUDA events between phases
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def phase(name):
+    if PHASE_HOOK is not None:
+        PHASE_HOOK(name)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+# ----------------------------------------------------------------------------- emission
+def emission_prepare(tuning, ma_neuron=None, dt=1.0):
+    """loglam[K,N] = ma*log(tuning*dt+1e-20), lam_sum[K] (reference decoder.py:39-43)."""
+    lib = _lib.load()
+    _f32(tuning, "tuning", 2)
+    K, N = tuning.shape
+    if ma_neuron is not None:
+        _f32(ma_neuron, "ma_neuron", 1)
+    loglam = torch.empty_like(tuning)
+    lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
+    check(lib.pmg_emission_prepare(K, N, _p(tuning), _p(ma_neuron), float(dt), _p(loglam), _p(lam_sum), _stream()),
+          "pmg_emission_prepare")
+    _count(1)
+    return loglam, lam_sum
+
+
+def lgamma_rowsum(y, ma_neuron=None):
+    lib = _lib.load()
+    _f32(y, "y", 2)
+    T, N = y.shape
+    out = torch.empty(T, dtype=torch.float32, device=y.device)
+    check(lib.pmg_emission_lgamma_rowsum(T, N, _p(y), N, _p(ma_neuron), _p(out), _stream()),
+          "pmg_emission_lgamma_rowsum")
+    _count(1)
+    return out
+
+
+def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None, impl=0):
+    """ll[T,K] (reference decoder.py:30-48,60-71)."""
+    lib = _lib.load()
+    _f32(y, "y", 2); _f32(loglam, "loglam", 2)
+    T, N = y.shape
+    K = loglam.shape[0]
+    if loglam.shape[1] != N:
+        raise ValueError("y has %d neurons but tuning has %d" % (N, loglam.shape[1]))
+    if out is None:
+        out = torch.empty((T, K), dtype=torch.float32, device=y.device)
+    check(lib.pmg_emission_poisson(T, N, K, _p(y), N, _p(loglam), _p(lam_sum), _p(lgam), _p(ma_latent),
+                                   _p(out), K, int(impl), _stream()), "pmg_emission_poisson")
+    _count(1)
+    return out
+
+
+def naive_bayes_normalize(ll, inplace=False):
+    """(log_post[T,K], lml_t[T]) (reference decoder.py:98-101)."""
+    lib = _lib.load()
+    _f32(ll, "ll", 2)
+    T, K = ll.shape
+    log_post = ll if inplace else torch.empty_like(ll)
+    lml = torch.empty(T, dtype=torch.float32, device=ll.device)
+    check(lib.pmg_naive_bayes_normalize(T, K, _p(ll), K, _p(log_post), K, _p(lml), _stream()),
+          "pmg_naive_bayes_normalize")
+    _count(1)
+    return log_post, lml
+
+
+# ----------------------------------------------------------------------------- transitions
+class MoveOperator:
+    """Device copy of the factored "move" transition + the 2x2 dynamics matrix."""
+
+    def __init__(self, host, M, device):
+        self.K = int(host["inv_z"].shape[0]) if host["kind"] == 0 else int(host["band_fwd"].shape[1])
+        self.kind, self.W = int(host["kind"]), int(host["W"])
+        self.M = np.asarray(M, dtype=np.float32).reshape(4)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.taps = dev(host["taps"]) if self.kind == 0 else None
+        self.inv_z = dev(host["inv_z"]) if self.kind == 0 else None
+        self.band_fwd = dev(host["band_fwd"]) if self.kind == 1 else None
+        self.band_bwd = dev(host["band_bwd"]) if self.kind == 1 else None
+
+    def cstruct(self):
+        s = PmgTransition()
+        s.K, s.kind, s.W = self.K, self.kind, self.W
+        s.taps = self.taps.data_ptr() if self.taps is not None else None
+        s.inv_z = self.inv_z.data_ptr() if self.inv_z is not None else None
+        s.band_fwd = self.band_fwd.data_ptr() if self.band_fwd is not None else None
+        s.band_bwd = self.band_bwd.data_ptr() if self.band_bwd is not None else None
+        for i in range(4):
+            s.M[i] = float(self.M[i])
+        return s
+
+
+def make_plan(T, core_begin, core_end, chunk_len, halo, left_exact, right_exact, likelihood_scale):
+    p = PmgScanPlan()
+    p.T, p.core_begin, p.core_end = int(T), int(core_begin), int(core_end)
+    p.chunk_len = int(chunk_len)
+    p.n_chain = int((core_end - core_begin + chunk_len - 1) // chunk_len)
+    p.halo = int(halo)
+    p.left_exact, p.right_exact = int(bool(left_exact)), int(bool(right_exact))
+    p.likelihood_scale = float(likelihood_scale)
+    return p
+
+
+def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None):
+    lib = _lib.load()
+    tr = op.cstruct()
+    n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
+    check(lib.pmg_forward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(carry_in), _p(alpha), _p(lmr),
+                          _p(halo_state), int(mode), _p(chain_ids), n_ids, _stream()), "pmg_forward")
+    _count(1)
+
+
+def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
+             beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None):
+    lib = _lib.load()
+    tr = op.cstruct()
+    n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
+    check(lib.pmg_backward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(alpha), _p(beta_in), _p(gamma),
+                           _p(gamma_lat), _p(dyn_marg), _p(r_out), _p(tw_partial), _p(beta_halo), _p(beta_end),
+                           int(mode), _p(chain_ids), n_ids, _stream()), "pmg_backward")
+    _count(1)
+
+
+def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1e-20):
+    lib = _lib.load()
+    check(lib.pmg_seam_check(int(n), int(length), C.c_void_p(est_ptr), int(ld_est), C.c_void_p(truth_ptr),
+                             int(ld_truth), float(floor_val), _p(err), _stream()), "pmg_seam_check")
+    _count(1)
+
+
+# ----------------------------------------------------------------------------- reductions over time
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def atb(A, B, out=None, impl=0):
+    """C[M,N] = sum_t A[t,:M]^T B[t,:N].  A and B may be row-offset views of 2-D tensors."""
+    lib = _lib.load()
+    if A.dim() != 2 or B.dim() != 2 or A.shape[0] != B.shape[0]:
+        raise ValueError("atb expects [T,M] and [T,N]")
+    for t, nm in ((A, "A"), (B, "B")):
+        if t.dtype != torch.float32 or not t.is_cuda or t.stride(1) != 1:
+            raise TypeError("%s must be a float32 CUDA tensor with unit inner stride" % nm)
+    T, M = A.shape
+    N = B.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    nbytes = lib.pmg_atb_workspace_bytes(T, M, N, int(impl))
+    ws = _workspace(nbytes, A.device)
+    check(lib.pmg_atb(T, M, N, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), N, _p(ws), ws.numel(), int(impl),
+                      _stream()), "pmg_atb")
+    _count(2)
+    return out
+
+
+def xi_finalize(G, logP, logM_host):
+    lib = _lib.load()
+    _f32(G, "G", 2); _f32(logP, "logP", 3)
+    K = logP.shape[1]
+    out = torch.empty((2, 2, K, K), dtype=torch.float32, device=G.device)
+    lm = (C.c_float * 4)(*[float(v) for v in np.asarray(logM_host, dtype=np.float32).reshape(4)])
+    check(lib.pmg_xi_finalize(K, _p(G), _p(logP), lm, _p(out), _stream()), "pmg_xi_finalize")
+    _count(1)
+    return out
+
+
+# ----------------------------------------------------------------------------- M-step
+class AdamState:
+    """optax.adam state (count, mu, nu) kept on the device across EM iterations
+    (reference core.py:662, fit_tuning_helper.py:131-132)."""
+
+    def __init__(self, params):
+        self.count = torch.zeros(1, dtype=torch.int32, device=params.device)
+        self.mu = torch.zeros_like(params)
+        self.nu = torch.zeros_like(params)
+
+
+def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, tol=1e-6, min_iters=5,
+               b1=0.9, b2=0.999, eps=1e-8):
+    """Runs the whole Adam loop on the device.  W and state are updated in place.
+    Returns device tensors (loss_hist[maxiter], err_hist[maxiter], n_iter[1] int32, final[2], tuning[K,N])."""
+    lib = _lib.load()
+    _f32(Phi, "Phi", 2); _f32(yw, "yw", 2); _f32(tw, "tw", 1); _f32(W, "W", 2)
+    K, B = Phi.shape
+    N = W.shape[1]
+    if W.shape[0] != B or yw.shape != (K, N) or tw.shape[0] != K:
+        raise ValueError("inconsistent M-step shapes")
+    dev = W.device
+    maxiter = int(maxiter)
+    loss_hist = torch.empty(maxiter, dtype=torch.float32, device=dev)
+    err_hist = torch.empty(maxiter, dtype=torch.float32, device=dev)
+    n_iter = torch.empty(1, dtype=torch.int32, device=dev)
+    final = torch.empty(2, dtype=torch.float32, device=dev)
+    tuning = torch.empty((K, N), dtype=torch.float32, device=dev)
+    nbytes = lib.pmg_mstep_workspace_bytes(K, B, N, maxiter)
+    ws = _workspace(nbytes, dev)
+    check(lib.pmg_mstep_adam(K, B, N, _p(Phi), _p(yw), _p(tw), float(prior_std), float(step_size), float(b1),
+                             float(b2), float(eps), maxiter, float(tol), int(min_iters), _p(W), _p(state.mu),
+                             _p(state.nu), _p(state.count), _p(loss_hist), _p(err_hist), _p(n_iter), _p(final),
+                             _p(tuning), _p(ws), ws.numel(), _stream()), "pmg_mstep_adam")
+    _count(1)
+    return loss_hist, err_hist, n_iter, final, tuning
+
+
+def tuning_softplus(Phi, W):
+    """softplus(Phi @ W) (reference fit_tuning_helper.py:11-25)."""
+    lib = _lib.load()
+    _f32(Phi, "Phi", 2); _f32(W, "W", 2)
+    K, B = Phi.shape
+    N = W.shape[1]
+    out = torch.empty((K, N), dtype=torch.float32, device=W.device)
+    check(lib.pmg_tuning_softplus(K, B, N, _p(Phi), _p(W), _p(out), _stream()), "pmg_tuning_softplus")
+    _count(1)
+    return out

@@ -1,0 +1,106 @@
+"""CPU-only tests: C-ABI surface, host-side logic, product/oracle separation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from poor_man_gplvm_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    hdr = open(os.path.join(ROOT, "include", "pmgplvm_b200.h")).read()
+    declared = set(re.findall(r"\b(pmg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(libpath)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from poor_man_gplvm_b200 import _lib
+    assert set(_lib.SIGNATURES) == declared
+    lib2 = _lib.load()
+    assert lib2.pmg_version() >= 100
+    assert lib2.pmg_error_string(-1) == b"bad argument"
+
+
+def test_struct_layouts_match_header():
+    from poor_man_gplvm_b200._lib import PmgScanPlan, PmgTransition
+    # int K,kind,W (+4 pad) ; 4 pointers ; float[4]
+    assert ctypes.sizeof(PmgTransition) == 16 + 32 + 16
+    # 4 x int64 ; 4 x int ; float (+4 pad)
+    assert ctypes.sizeof(PmgScanPlan) == 32 + 16 + 8
+
+
+def test_transition_and_basis_match_oracle():
+    from poor_man_gplvm_b200 import gp_kernel as gpk
+    for K, mv in ((50, 1.0), (100, 2.5)):
+        P, logP, M, logM = gpk.create_transition_prob_1d(np.arange(K), np.arange(2), mv, 0.02, 0.03)
+        Po, logPo, Mo, logMo = ref.create_transition_prob_1d(K, mv, 0.02, 0.03, dtype=np.float32)
+        assert np.allclose(P, Po, atol=1e-7) and np.allclose(logP, logPo, atol=1e-5)
+        assert np.allclose(M, Mo) and np.allclose(logM, logMo)
+    B = gpk.generate_basis(10.0, 100)
+    Bo = ref.generate_basis(10.0, 100, dtype=np.float32)
+    assert B.shape == Bo.shape == (100, 18)                       # B=18 at K=100, ls=10
+    assert np.allclose(np.abs(B), np.abs(Bo), atol=1e-4)          # SVD sign ambiguity
+
+
+@pytest.mark.parametrize("K,mv", [(40, 1.0), (64, 3.0)])
+def test_move_operator_factorisation_reconstructs_P0(K, mv):
+    from poor_man_gplvm_b200 import gp_kernel as gpk
+    P, *_ = gpk.create_transition_prob_1d(np.arange(K), np.arange(2), mv)
+    h = gpk.move_operator_host(K, mv)
+    assert h["kind"] == 0 and h["W"] <= int(10.2 * mv)
+    x = np.arange(K)
+    d = np.abs(x[:, None] - x[None, :])
+    rec = np.where(d <= h["W"], h["taps"][np.minimum(d, h["W"])], 0) * h["inv_z"][:, None]
+    assert np.max(np.abs(rec - P[0])) < 1e-7
+    rng = np.random.default_rng(0)
+    ck = rng.random((K, K)) * (d <= 5)
+    ck[np.arange(K), np.arange(K)] += 0.1
+    h = gpk.move_operator_host(K, mv, ck)
+    P0 = ck / ck.sum(axis=1, keepdims=True)
+    assert h["kind"] == 1 and h["W"] == 5
+    W = h["W"]
+    for j in range(2 * W + 1):
+        for xx in range(K):
+            src = xx - W + j
+            if 0 <= src < K:
+                assert np.isclose(h["band_fwd"][j, xx], P0[src, xx])
+                assert np.isclose(h["band_bwd"][j, xx], P0[xx, src])
+
+
+def test_plan_chunks_bounds():
+    from poor_man_gplvm_b200.estep import plan_chunks
+    assert plan_chunks(1000, 256, 148) == 1000                    # short sequences: one exact chain
+    c = plan_chunks(10 ** 6, 256, 148)
+    assert c >= 4 * 256 and (10 ** 6 + c - 1) // c <= 148 * 8
+    assert plan_chunks(5000, 0, 148) == 5000
+
+
+def test_model_constructs_on_cpu_and_fails_loudly_without_gpu():
+    import torch
+    import poor_man_gplvm_b200 as pmg
+    m = pmg.PoissonGPLVMJump1D(8, 20, tuning_lengthscale=4.0)
+    assert m.tuning.shape == (20, 8) and m.params.shape == (m.n_basis, 8)
+    assert np.all(m.tuning > 0) and m.tuning_basis[:, 0].tolist() == [1.0] * 20
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            m.decode_latent_naive_bayes(np.zeros((5, 8), np.float32))
+
+
+def test_product_sources_never_touch_the_oracle():
+    pkg = os.path.join(ROOT, "poor_man_gplvm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "/root/reference" not in src, f
