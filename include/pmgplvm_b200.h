@@ -48,10 +48,25 @@ int pmg_emission_prepare(int K, int N, const float* tuning, const float* ma_neur
 int pmg_emission_lgamma_rowsum(int64_t T, int N, const float* y, int64_t ldy,
                                const float* ma_neuron, float* lgam, pmg_stream_t stream);
 
-/* impl: 0 = default (tcgen05 when the shape allows it), 1 = CUDA-core fp32 tiles (cross-check). */
+/* fp32 operands on CUDA-core tiles: for counts that are not exact in fp16 (non-integer y,
+ * decoder.py:37-38) and as the cross-check of the tensor-core kernel below. */
 int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,
                          const float* lam_sum, const float* lgam, const float* ma_latent,
-                         float* ll, int64_t ldll, int impl, pmg_stream_t stream);
+                         float* ll, int64_t ldll, pmg_stream_t stream);
+
+/* Tensor-core path (tcgen05 kind::f16, TMA-fed, fp32 accumulation in TMEM).
+ * y16: fp16 copy of the counts, [T, ld16] with ld16 % 8 == 0 and zero padding; *inexact_count (device)
+ *      = number of entries that fp16 does not represent exactly (caller must use the fp32 path if > 0).
+ * loglam16: [2, Kpad, ld16] fp16, hi and lo pieces of ma*log(lam) (hi + lo carries 22 bits);
+ *      Kpad = ceil(K / BN) * BN with BN = pmg_emission_tile_n(K); padding rows/columns are zero. */
+int pmg_counts_to_f16(int64_t T, int N, const float* y, int64_t ldy, void* y16, int64_t ld16,
+                      int* inexact_count, pmg_stream_t stream);
+int pmg_emission_tile_n(int K);
+int pmg_emission_prepare_f16(int K, int N, const float* tuning, const float* ma_neuron, float dt, int Kpad,
+                             int64_t ld16, void* loglam16, float* lam_sum, pmg_stream_t stream);
+int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16, int64_t ld16, const void* loglam16,
+                             int Kpad, const float* lam_sum, const float* lgam, const float* ma_latent,
+                             float* ll, int64_t ldll, pmg_stream_t stream);
 
 /* -------------------------------------------------------------------- E3 --
  * Naive-Bayes normalisation, decoder.py:88-102: lml_t = logsumexp_k ll[t,:],

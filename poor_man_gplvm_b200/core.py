@@ -293,9 +293,8 @@ class PoissonGPLVMJump1D:
         if dt_arr.ndim > 0 and dt_arr.size > 1 and not np.all(dt_arr == dt_arr.flat[0]):
             raise NotImplementedError("per-bin dt_l is not on the CUDA path yet (SURVEY F4)")
         dt = float(dt_arr.flat[0]) if dt_arr.size else 1.0
-        loglam, lam_sum = ops.emission_prepare(self._dev(tuning), ma_n, dt)
         lgam = ops.lgamma_rowsum(y_dev, ma_n)
-        ll = ops.emission_poisson(y_dev, loglam, lam_sum, lgam, ma_l)
+        ll = ops.emission(y_dev, self._dev(tuning), lgam, ma_n, ma_l, dt, y16=ops.CountsF16(y_dev))
         log_post, lml = ops.naive_bayes_normalize(ll)
         conv = (lambda t: t) if return_device else self._host
         return {'log_posterior_latent': conv(log_post),

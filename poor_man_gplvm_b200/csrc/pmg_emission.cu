@@ -49,7 +49,8 @@ __global__ void lgamma_rowsum_kernel(int64_t T, int N, const float* __restrict__
   if (lane == 0) out[t] = acc;
 }
 
-// ---- CUDA-core fp32 tile GEMM with the emission epilogue (cross-check path) ----
+// ---- CUDA-core fp32 tile GEMM with the emission epilogue: used when the counts are not exactly
+// representable in fp16 (non-integer "counts", decoder.py:37-38) and as the cross-check of the tcgen05 kernel ----
 constexpr int EM_BM = 128, EM_BN = 64, EM_BK = 16;
 
 __global__ void __launch_bounds__(256) emission_simt_kernel(int64_t T, int N, int K,
@@ -141,10 +142,6 @@ __global__ void nb_normalize_kernel(int64_t T, int K, const float* __restrict__ 
 
 }  // namespace pmg
 
-int pmg_emission_tc_launch(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,
-                           const float* lam_sum, const float* lgam, const float* ma_latent, float* ll,
-                           int64_t ldll, cudaStream_t st);   // pmg_gemm_tc.cu (returns PMG_ERR_UNSUPPORTED_SHAPE if n/a)
-
 extern "C" int pmg_emission_prepare(int K, int N, const float* tuning, const float* ma_neuron, float dt,
                                     float* loglam, float* lam_sum, pmg_stream_t stream) {
   if (K <= 0 || N <= 0 || !tuning || !loglam || !lam_sum) return PMG_ERR_BAD_ARG;
@@ -163,13 +160,9 @@ extern "C" int pmg_emission_lgamma_rowsum(int64_t T, int N, const float* y, int6
 
 extern "C" int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,
                                     const float* lam_sum, const float* lgam, const float* ma_latent, float* ll,
-                                    int64_t ldll, int impl, pmg_stream_t stream) {
+                                    int64_t ldll, pmg_stream_t stream) {
   if (T <= 0 || N <= 0 || K <= 0 || !y || !loglam || !lam_sum || !lgam || !ll) return PMG_ERR_BAD_ARG;
   if (ldy < N || ldll < K) return PMG_ERR_BAD_ARG;
-  if (impl == 0) {
-    int rc = pmg_emission_tc_launch(T, N, K, y, ldy, loglam, lam_sum, lgam, ma_latent, ll, ldll, (cudaStream_t)stream);
-    if (rc != PMG_ERR_UNSUPPORTED_SHAPE) return rc;
-  }
   dim3 grid(pmg::cdiv(T, pmg::EM_BM), pmg::cdiv(K, pmg::EM_BN));
   pmg::emission_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, N, K, y, ldy, loglam, lam_sum, lgam,
                                                                    ma_latent, ll, ldll);

@@ -1,11 +1,306 @@
-// tcgen05 / TMA tensor-core GEMMs (emission and time-reduction).  Placeholder until the
-// tensor-core kernels land: reports "unsupported" so callers use the CUDA-core tiles.
+// Tensor-core (tcgen05 + TMEM + TMA) GEMMs of the EM hot path.
+//
+//  * emission (reference poor_man_gplvm/decoder.py:30-48, :60-71):
+//      ll[t,k] = sum_n y[t,n] * loglam[k,n] - lam_sum[k] - lgam[t]
+//    y is stored once as fp16 (spike counts are exact in fp16 up to 2048); loglam is split into
+//    two fp16 pieces (hi + lo = 22 significant bits), both K-major, so the product needs two
+//    kind::f16 MMAs per K step accumulating in fp32 in TMEM.
+//  * time reduction (reference fit_tuning_helper.py:28-42):
+//      yw[k,n] = sum_t gamma[t,k] * y[t,n]
+//    both operands have time as the slow axis (MN-major UMMA operands); gamma arrives as two
+//    fp16 pieces written by the backward scan.
+//
+// Persistent, warp-specialised CTAs: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
 #include "pmg_common.cuh"
+#include "pmg_tc.cuh"
 
-int pmg_emission_tc_launch(int64_t, int, int, const float*, int64_t, const float*, const float*, const float*,
-                           const float*, float*, int64_t, cudaStream_t) {
-  return PMG_ERR_UNSUPPORTED_SHAPE;
+namespace pmg {
+
+using namespace tc;
+
+constexpr int TC_BM = 128;        // rows of the accumulator tile (TMEM lanes)
+constexpr int TC_BK = 64;         // fp16 elements per K block = one 128-byte swizzle row
+constexpr int TC_THREADS = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+
+// ---------------------------------------------------------------------------------------------
+// conversions
+// ---------------------------------------------------------------------------------------------
+__global__ void counts_to_f16_kernel(int64_t T, int N, const float* __restrict__ y, int64_t ldy,
+                                     __half* __restrict__ y16, int64_t ld16, int* __restrict__ inexact) {
+  const int64_t total = T * ld16;
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / ld16;
+    const int n = (int)(i - t * ld16);
+    float v = 0.f;
+    if (n < N) v = y[(size_t)t * ldy + n];
+    const __half h = __float2half_rn(v);
+    if (__half2float(h) != v) ++bad;
+    y16[i] = h;
+  }
+  if (__syncthreads_or(bad)) {
+    if (bad) atomicAdd(inexact, bad);
+  }
 }
+
+// loglam pieces [2][Kpad][ld16]; rows >= K and columns >= N are zero.  One CTA per padded row.
+__global__ void emission_prepare_f16_kernel(int K, int N, const float* __restrict__ tuning,
+                                            const float* __restrict__ ma_neuron, float dt, int Kpad, int64_t ld16,
+                                            __half* __restrict__ L16, float* __restrict__ lam_sum) {
+  const int k = blockIdx.x;
+  __half* hi = L16 + (size_t)k * ld16;
+  __half* lo = L16 + ((size_t)Kpad + k) * ld16;
+  double acc = 0.0;
+  for (int n = threadIdx.x; n < (int)ld16; n += blockDim.x) {
+    float v = 0.f;
+    if (k < K && n < N) {
+      const float m = ma_neuron ? ma_neuron[n] : 1.f;
+      const float lam = tuning[(size_t)k * N + n] * dt + kLamFloor;
+      v = m * logf(lam);
+      acc += (double)(m * lam);
+    }
+    const __half h = __float2half_rn(v);
+    hi[n] = h;
+    lo[n] = __float2half_rn(v - __half2float(h));
+  }
+  if (k >= K) return;
+  acc = warp_sum_d(acc);
+  __shared__ double sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
+    lam_sum[k] = (float)s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// emission: K-major operands
+// ---------------------------------------------------------------------------------------------
+struct EmissionTcParams {
+  int64_t T;
+  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages;
+  uint32_t idesc, tmem_cols;
+  const float* lam_sum;
+  const float* lgam;
+  const float* ma_latent;
+  float* ll;
+  int64_t ldll;
+};
+
+constexpr int EM_PB = 2;   // fp16 pieces of loglam
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const EmissionTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;
+  const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
+  const uint32_t stage_bytes = TC_A_BYTES + EM_PB * b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = p.n_mtiles * p.n_ntiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_ntiles, nt = tile % p.n_ntiles;
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);
+          tma_load_2d(sA, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+#pragma unroll
+          for (int pc = 0; pc < EM_PB; ++pc)
+            tma_load_2d(sA + TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kb * TC_BK, pc * p.Kpad + nt * BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+          for (int pc = 0; pc < EM_PB; ++pc) {
+            const uint32_t sB = sA + TC_A_BYTES + pc * b_bytes;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(sA + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(sB + k * 32, 16, 1024);
+              mma_f16_ss(d_tmem, ad, bd, p.idesc, (kb | pc | k) != 0);
+            }
+          }
+          mma_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / p.n_ntiles, nt = tile % p.n_ntiles;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[buf], acc_phase);
+      tc_fence_after();
+      const int64_t t = (int64_t)mt * TC_BM + q * 32 + lane;
+      const bool t_ok = t < p.T;
+      const float lg = t_ok ? p.lgam[t] : 0.f;
+      float* orow = p.ll + (size_t)(t_ok ? t : 0) * p.ldll;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      const bool vec_ok = (p.ldll & 3) == 0;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(taddr + c0, r);
+        tmem_ld_wait();
+        const int k0 = nt * BN + c0;
+        if (t_ok && k0 < p.K) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = k0 + j;
+            float x = __uint_as_float(r[j]);
+            if (k < p.K) {
+              x = x - __ldg(p.lam_sum + k) - lg;
+              if (p.ma_latent && __ldg(p.ma_latent + k) == 0.f) x = kVeryNegLL;
+            }
+            v[j] = x;
+          }
+          if (vec_ok && k0 + 16 <= p.K) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(orow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (k0 + j < p.K) orow[k0 + j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+static uint32_t pow2_cols(int c) {
+  uint32_t v = 32;
+  while ((int)v < c) v <<= 1;
+  return v;
+}
+
+}  // namespace pmg
+
+// BN = accumulator columns per tile: K split into ceil(K/256) tiles, rounded up to 16
+extern "C" int pmg_emission_tile_n(int K) {
+  if (K <= 0) return 0;
+  const int nt = (K + 255) / 256;
+  int bn = (K + nt - 1) / nt;
+  bn = (bn + 15) / 16 * 16;
+  return bn;
+}
+
+extern "C" int pmg_counts_to_f16(int64_t T, int N, const float* y, int64_t ldy, void* y16, int64_t ld16,
+                                 int* inexact_count, pmg_stream_t stream) {
+  if (T <= 0 || N <= 0 || !y || !y16 || !inexact_count || ldy < N || ld16 < N || (ld16 & 7)) return PMG_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PMG_CUDA_CHECK(cudaMemsetAsync(inexact_count, 0, sizeof(int), st));
+  pmg::counts_to_f16_kernel<<<148 * 8, 256, 0, st>>>(T, N, y, ldy, (__half*)y16, ld16, inexact_count);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_emission_prepare_f16(int K, int N, const float* tuning, const float* ma_neuron, float dt,
+                                        int Kpad, int64_t ld16, void* loglam16, float* lam_sum,
+                                        pmg_stream_t stream) {
+  if (K <= 0 || N <= 0 || !tuning || !loglam16 || !lam_sum || Kpad < K || ld16 < N || (ld16 & 7)) return PMG_ERR_BAD_ARG;
+  pmg::emission_prepare_f16_kernel<<<Kpad, 128, 0, (cudaStream_t)stream>>>(K, N, tuning, ma_neuron, dt, Kpad, ld16,
+                                                                          (__half*)loglam16, lam_sum);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16, int64_t ld16,
+                                        const void* loglam16, int Kpad, const float* lam_sum, const float* lgam,
+                                        const float* ma_latent, float* ll, int64_t ldll, pmg_stream_t stream) {
+  using namespace pmg;
+  if (T <= 0 || N <= 0 || K <= 0 || !y16 || !loglam16 || !lam_sum || !lgam || !ll) return PMG_ERR_BAD_ARG;
+  if (ld16 < N || (ld16 & 7) || ldll < K) return PMG_ERR_BAD_ARG;
+  if (((uintptr_t)y16 & 15) || ((uintptr_t)loglam16 & 15)) return PMG_ERR_ALIGNMENT;
+  const int BN = pmg_emission_tile_n(K);
+  const int n_ntiles = (K + BN - 1) / BN;
+  if (Kpad != n_ntiles * BN) return PMG_ERR_BAD_ARG;
+  if (T > ((int64_t)1 << 31) - 256) return PMG_ERR_UNSUPPORTED_SHAPE;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_f16(&tmA, y16, (uint64_t)T, (uint64_t)ld16, (uint64_t)ld16, TC_BM);
+  if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+  rc = make_tmap_f16(&tmB, loglam16, (uint64_t)EM_PB * Kpad, (uint64_t)ld16, (uint64_t)ld16, (uint32_t)BN);
+  if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+
+  EmissionTcParams p;
+  p.T = T; p.K = K; p.Kpad = Kpad; p.BN = BN;
+  p.n_kblocks = (int)((ld16 + TC_BK - 1) / TC_BK);
+  p.n_mtiles = (int)((T + TC_BM - 1) / TC_BM);
+  p.n_ntiles = n_ntiles;
+  const uint32_t stage_bytes = TC_A_BYTES + EM_PB * BN * TC_BK * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
+  p.stages = stages;
+  p.idesc = make_idesc_f16(TC_BM, BN, 0, 0, 0);
+  p.tmem_cols = pow2_cols(2 * BN);
+  p.lam_sum = lam_sum; p.lgam = lgam; p.ma_latent = ma_latent; p.ll = ll; p.ldll = ldll;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  cudaStream_t st = (cudaStream_t)stream;
+  PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  PMG_CUDA_CHECK(cudaGetDevice(&dev));
+  PMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tiles = p.n_mtiles * p.n_ntiles;
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  emission_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+// time-reduction GEMM on tensor cores: not yet available (callers use the CUDA-core tiles)
 int64_t pmg_atb_tc_workspace_bytes(int64_t, int, int) { return 0; }
 int pmg_atb_tc_launch(int64_t, int, int, const float*, int64_t, const float*, int64_t, float*, int64_t, void*,
                       int64_t, cudaStream_t) {

@@ -85,7 +85,8 @@ __global__ void xi_finalize_kernel(int K, const float* __restrict__ G, const flo
   const int x = (int)((i % KK) / K), xn = (int)(i % K);
   const float g = G[((size_t)d * K + x) * (2 * K) + (size_t)dn * K + xn];
   const float lm = d == 0 ? (dn == 0 ? lm00 : lm01) : (dn == 0 ? lm10 : lm11);
-  log_acc[i] = lm + logP[(size_t)dn * KK + (size_t)x * K + xn] + logf(g);
+  // floor keeps rows of masked latent bins finite (the reference's log-space accumulator never reaches -inf)
+  log_acc[i] = lm + logP[(size_t)dn * KK + (size_t)x * K + xn] + logf(fmaxf(g, 1e-37f));
 }
 
 static int atb_splits(int64_t T, int M, int N) {

@@ -61,6 +61,7 @@ class EStep:
         S = self.plan.n_chain
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.lgam = ops.lgamma_rowsum(y, ma_neuron)
+        self.y16 = ops.CountsF16(y) if emission_impl == 0 else None
         self.ll = torch.empty((self.T, self.K), **f32)
         self.alpha = torch.empty((self.T, 2, self.K), **f32)
         self.lmr = torch.empty(self.T, **f32)
@@ -73,9 +74,8 @@ class EStep:
 
     # -- pieces ---------------------------------------------------------------------------
     def emission(self, tuning):
-        loglam, lam_sum = ops.emission_prepare(tuning, self.ma_neuron, 1.0)
-        ops.emission_poisson(self.y, loglam, lam_sum, self.lgam, self.ma_latent, out=self.ll,
-                             impl=self.emission_impl)
+        ops.emission(self.y, tuning, self.lgam, self.ma_neuron, self.ma_latent, 1.0, out=self.ll, y16=self.y16,
+                     impl=self.emission_impl)
         return self.ll
 
     def _check_fwd(self, n, first_chain=1):

@@ -78,8 +78,8 @@ def lgamma_rowsum(y, ma_neuron=None):
     return out
 
 
-def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None, impl=0):
-    """ll[T,K] (reference decoder.py:30-48,60-71)."""
+def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None):
+    """ll[T,K] from fp32 operands on CUDA-core tiles (reference decoder.py:30-48,60-71)."""
     lib = _lib.load()
     _f32(y, "y", 2); _f32(loglam, "loglam", 2)
     T, N = y.shape
@@ -89,9 +89,74 @@ def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None, impl=0)
     if out is None:
         out = torch.empty((T, K), dtype=torch.float32, device=y.device)
     check(lib.pmg_emission_poisson(T, N, K, _p(y), N, _p(loglam), _p(lam_sum), _p(lgam), _p(ma_latent),
-                                   _p(out), K, int(impl), _stream()), "pmg_emission_poisson")
+                                   _p(out), K, _stream()), "pmg_emission_poisson")
     _count(1)
     return out
+
+
+class CountsF16:
+    """fp16 copy of the spike counts for the tensor-core kernels ([T, ld16], zero padded)."""
+
+    def __init__(self, y):
+        lib = _lib.load()
+        _f32(y, "y", 2)
+        self.T, self.N = y.shape
+        self.ld = (self.N + 7) // 8 * 8
+        self.data = torch.empty((self.T, self.ld), dtype=torch.float16, device=y.device)
+        self._inexact = torch.zeros(1, dtype=torch.int32, device=y.device)
+        check(lib.pmg_counts_to_f16(self.T, self.N, _p(y), self.N, _p(self.data), self.ld, _p(self._inexact),
+                                    _stream()), "pmg_counts_to_f16")
+        _count(1)
+        self._exact = None
+
+    @property
+    def exact(self):
+        """True when every count is exactly representable in fp16 (integers up to 2048)."""
+        if self._exact is None:
+            self._exact = int(self._inexact.item()) == 0
+        return self._exact
+
+
+def emission_tile_n(K):
+    return int(_lib.load().pmg_emission_tile_n(int(K)))
+
+
+def emission_prepare_f16(tuning, y16, ma_neuron=None, dt=1.0):
+    """(loglam16 [2,Kpad,ld16] fp16 hi/lo pieces, lam_sum[K])."""
+    lib = _lib.load()
+    _f32(tuning, "tuning", 2)
+    K, N = tuning.shape
+    if N != y16.N:
+        raise ValueError("y has %d neurons but tuning has %d" % (y16.N, N))
+    bn = emission_tile_n(K)
+    Kpad = (K + bn - 1) // bn * bn
+    L16 = torch.empty((2, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
+    lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
+    check(lib.pmg_emission_prepare_f16(K, N, _p(tuning), _p(ma_neuron), float(dt), Kpad, y16.ld, _p(L16),
+                                       _p(lam_sum), _stream()), "pmg_emission_prepare_f16")
+    _count(1)
+    return L16, lam_sum
+
+
+def emission_poisson_f16(y16, L16, lam_sum, lgam, K, ma_latent=None, out=None):
+    """ll[T,K] on the tensor cores (tcgen05 kind::f16, fp32 accumulation)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((y16.T, K), dtype=torch.float32, device=L16.device)
+    check(lib.pmg_emission_poisson_f16(y16.T, y16.N, K, _p(y16.data), y16.ld, _p(L16), L16.shape[1], _p(lam_sum),
+                                       _p(lgam), _p(ma_latent), _p(out), out.stride(0), _stream()),
+          "pmg_emission_poisson_f16")
+    _count(1)
+    return out
+
+
+def emission(y, tuning, lgam, ma_neuron=None, ma_latent=None, dt=1.0, out=None, y16=None, impl=0):
+    """Dispatch: tensor cores when the counts are fp16-exact (impl=0), else / impl=1 the fp32 tiles."""
+    if impl == 0 and y16 is not None and y16.exact:
+        L16, lam_sum = emission_prepare_f16(tuning, y16, ma_neuron, dt)
+        return emission_poisson_f16(y16, L16, lam_sum, lgam, tuning.shape[0], ma_latent, out=out)
+    loglam, lam_sum = emission_prepare(tuning, ma_neuron, dt)
+    return emission_poisson(y, loglam, lam_sum, lgam, ma_latent, out=out)
 
 
 def naive_bayes_normalize(ll, inplace=False):

@@ -32,7 +32,8 @@ def ops():
 
 
 # ----------------------------------------------------------------------------- emission / NB
-@pytest.mark.parametrize("T,N,K", [(1, 5, 3), (257, 37, 53), (1000, 30, 100), (3000, 200, 100), (513, 130, 400)])
+@pytest.mark.parametrize("T,N,K", [(1, 5, 3), (257, 37, 53), (1000, 30, 100), (3000, 200, 100), (513, 130, 400),
+                                   (40000, 500, 400), (300, 70, 600)])
 @pytest.mark.parametrize("impl", [0, 1])
 def test_emission_matches_oracle(ops, T, N, K, impl):
     d = make_dataset(T, N, K, seed=T + N)
@@ -40,9 +41,11 @@ def test_emission_matches_oracle(ops, T, N, K, impl):
     ma_n = (rng.random(N) > 0.15).astype(np.float32)
     ma_l = (rng.random(K) > 0.1).astype(np.float32)
     want = ref.get_loglikelihood_ma_all(d["y"].astype(np.float64), d["tuning_true"].astype(np.float64), ma_n, ma_l)
-    loglam, lam_sum = ops.emission_prepare(dev(d["tuning_true"]), dev(ma_n), 1.0)
-    lgam = ops.lgamma_rowsum(dev(d["y"]), dev(ma_n))
-    got = host(ops.emission_poisson(dev(d["y"]), loglam, lam_sum, lgam, dev(ma_l), impl=impl))
+    y = dev(d["y"])
+    lgam = ops.lgamma_rowsum(y, dev(ma_n))
+    y16 = ops.CountsF16(y)
+    assert y16.exact
+    got = host(ops.emission(y, dev(d["tuning_true"]), lgam, dev(ma_n), dev(ma_l), y16=y16, impl=impl))
     live = ma_l.astype(bool)
     assert np.all(got[:, ~live] == np.float32(-1e20))
     scale = np.maximum(1.0, np.abs(want[:, live]))
@@ -58,9 +61,10 @@ def test_emission_noninteger_and_large_counts(ops):
     tun[3, 4] = 0.0                                                   # zero rate -> log(1e-20)
     ones_n, ones_k = np.ones(N, np.float32), np.ones(K, np.float32)
     want = ref.get_loglikelihood_ma_all(y.astype(np.float64), tun.astype(np.float64), ones_n, ones_k)
-    loglam, lam_sum = ops.emission_prepare(dev(tun), None, 1.0)
     lgam = ops.lgamma_rowsum(dev(y), None)
-    got = host(ops.emission_poisson(dev(y), loglam, lam_sum, lgam, None))
+    y16 = ops.CountsF16(dev(y))
+    assert not y16.exact                                              # routed to the fp32 tiles
+    got = host(ops.emission(dev(y), dev(tun), lgam, y16=y16))
     assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 3e-6
 
 
