@@ -115,12 +115,14 @@ int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, const float
                 const int* chain_ids, int n_ids, pmg_stream_t stream);
 
 /* gamma:      [T, 2, K] or NULL; gamma_lat: [T, K] or NULL (sum over dynamics); dyn_marg: [T,2] or NULL
+ * gamma16:    [2, T, ldg] fp16 or NULL: hi/lo pieces of gamma_lat (ldg % 8 == 0; padding columns are not
+ *             written: zero them once) for pmg_atb_f16
  * r_out:      [T, 2, K] or NULL (r[t] = L_t*beta_t/c_t, the right factor of the transition counts)
  * tw_partial: [n_chain, K] or NULL (per-chain sum_t gamma_lat)
  * beta_in:    [2,K] or NULL (ones);  beta_halo / beta_end: [n_chain, 2, K]. */
 int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
                  const float* alpha, const float* beta_in, float* gamma, float* gamma_lat,
-                 float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo, float* beta_end,
+                 void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo, float* beta_end,
                  int mode, const int* chain_ids, int n_ids, pmg_stream_t stream);
 
 /* err[i] = max relative difference between est[i,:] and truth[i,:] over entries > floor.
@@ -138,6 +140,16 @@ int64_t pmg_atb_workspace_bytes(int64_t T, int M, int N, int impl);
 int pmg_atb(int64_t T, int M, int N, const float* A, int64_t lda, const float* B, int64_t ldb,
             float* C, int64_t ldc, void* workspace, int64_t workspace_bytes, int impl,
             pmg_stream_t stream);
+
+/* Tensor-core time reduction for the sufficient statistics (tcgen05 kind::f16, both operands
+ * MN-major, split over time, fixed-order fp64 reduction of the splits):
+ *   yw[k,n] = sum_t (g16[0,t,k] + g16[1,t,k]) * y16[t,n]
+ * g16: [2, T, ldg] fp16 pieces of the posterior (pmg_split_f16 or pmg_backward's gamma16);
+ * y16: [T, ldy16] fp16 counts (pmg_counts_to_f16). */
+int pmg_split_f16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16, pmg_stream_t stream);
+int64_t pmg_atb_f16_workspace_bytes(int64_t T, int K, int N);
+int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
+                float* yw, void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
 
 /* log_acc[d,d',x,x'] = logM[d,d'] + logP_{d'}[x,x'] + log G[(d,x),(d',x')]   (G = alpha^T r, [2K,2K]):
  * decoder.py:221's accumulator; using the analytic log kernel keeps deep tails finite.

@@ -80,19 +80,32 @@ class EMLoop:
             raise ValueError("params shape %s does not match basis %s" % (tuple(self.W.shape), tuple(self.Phi.shape)))
         self.state = ops.AdamState(self.W)
         self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len)
-        self.gamma_lat = torch.exp(model._dev(log_posterior_init))
-        if self.gamma_lat.shape != (y_dev.shape[0], op.K):
+        gamma_lat = torch.exp(model._dev(log_posterior_init))
+        if gamma_lat.shape != (y_dev.shape[0], op.K):
             raise ValueError("log_posterior_init must be [T, n_latent_bin]")
-        self.tw = self.gamma_lat.sum(dim=0, dtype=torch.float64).to(torch.float32)
+        self.tw = gamma_lat.sum(dim=0, dtype=torch.float64).to(torch.float32)
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
+        # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
+        self.use_tc = self.es.y16 is not None and self.es.y16.exact
+        if self.use_tc:
+            self.gamma16 = ops.split_f16(gamma_lat)
+            self.gamma_lat = None
+        else:
+            self.gamma16 = None
+            self.gamma_lat = gamma_lat
 
-    def iteration(self, want_gamma=False, want_dyn=False):
-        yw = ops.atb(self.gamma_lat, self.y)                       # reference core.py:807
+    def iteration(self, want_gamma=False, want_dyn=False, want_gamma_lat=False):
+        """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path)."""
+        if self.use_tc:
+            yw = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)  # reference core.py:807
+        else:
+            yw = ops.atb(self.gamma_lat, self.y)
         ops.phase("stats")
         m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
                                self.maxiter, self.tol)             # reference core.py:810
         ops.phase("mstep")
-        res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=True, want_dyn=want_dyn, want_r=False)
+        res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
+                          want_dyn=want_dyn, want_r=False, gamma16=self.gamma16)
         self.gamma_lat, self.tw = res.gamma_lat, res.tw            # reference core.py:668
         return res, m_res
 
@@ -367,7 +380,7 @@ class PoissonGPLVMJump1D:
         for i in range(n_iter):
             last = i == n_iter - 1
             snap = (i % save_every == 0)
-            res, m_res = loop.iteration(want_gamma=(last or snap), want_dyn=last)
+            res, m_res = loop.iteration(want_gamma=(last or snap), want_dyn=last, want_gamma_lat=last)
             m_hist.append(m_res)
             tuning = m_res[4]
             lml_dev.append(res.log_marginal)

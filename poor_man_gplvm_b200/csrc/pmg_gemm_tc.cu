@@ -300,7 +300,225 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   return PMG_OK;
 }
 
-// time-reduction GEMM on tensor cores: not yet available (callers use the CUDA-core tiles)
+// ---------------------------------------------------------------------------------------------
+// time reduction: yw[k,n] = sum_t gamma[t,k] * y[t,n]   (both operands MN-major, time = UMMA K)
+// accumulator tile: lanes = neurons (M = 128), columns = latent bins (N = BN, multiple of 64)
+// ---------------------------------------------------------------------------------------------
+namespace pmg {
+
+constexpr int AT_BKT = 32;                       // time bins per pipeline stage
+constexpr int AT_BOX_BYTES = AT_BKT * 128;       // one TMA box: 32 rows x 64 halves
+constexpr int AT_PG = 2;                         // fp16 pieces of gamma
+
+struct AtbTcParams {
+  int64_t T, t_per_split;
+  int K, N, BN, n_mtiles, n_ntiles, splits, stages;
+  uint32_t tmem_cols;
+  float* partial;    // [splits][K][N]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG,
+              const AtbTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int mt = blockIdx.x, nt = blockIdx.y, sp = blockIdx.z;
+  const int k_base = nt * p.BN;
+  int bn = p.K - k_base;                         // columns of this tile, rounded up to the 64-wide atoms
+  bn = (bn + 63) / 64 * 64;
+  if (bn > p.BN) bn = p.BN;
+  const int n_boxes_b = bn / 64;
+  const uint32_t a_bytes = 2 * AT_BOX_BYTES;
+  const uint32_t b_piece_bytes = (uint32_t)(p.BN / 64) * AT_BOX_BYTES;
+  const uint32_t stage_bytes = a_bytes + AT_PG * b_piece_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmG); }
+  if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t t_begin = (int64_t)sp * p.t_per_split;
+  int64_t t_end = t_begin + p.t_per_split;
+  if (t_end > p.T) t_end = p.T;
+  const int n_tb = t_end > t_begin ? (int)((t_end - t_begin + AT_BKT - 1) / AT_BKT) : 0;
+  const uint32_t tx_bytes = a_bytes + AT_PG * (uint32_t)n_boxes_b * AT_BOX_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tb = 0; tb < n_tb; ++tb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sA = smem + (size_t)stage * stage_bytes;
+        const int t0 = (int)(t_begin + (int64_t)tb * AT_BKT);
+        mbar_arrive_expect_tx(&full[stage], tx_bytes);
+        tma_load_2d(sA, &tmY, &full[stage], mt * TC_BM, t0);
+        tma_load_2d(sA + AT_BOX_BYTES, &tmY, &full[stage], mt * TC_BM + 64, t0);
+        for (int pc = 0; pc < AT_PG; ++pc)
+          for (int b = 0; b < n_boxes_b; ++b)
+            tma_load_2d(sA + a_bytes + pc * b_piece_bytes + b * AT_BOX_BYTES, &tmG, &full[stage], k_base + b * 64,
+                        (int)(pc * p.T) + t0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(TC_BM, bn, 1, 1, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int tb = 0; tb < n_tb; ++tb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+        for (int pc = 0; pc < AT_PG; ++pc) {
+          const uint32_t sB = sA + a_bytes + pc * b_piece_bytes;
+#pragma unroll
+          for (int k = 0; k < AT_BKT / 16; ++k) {
+            // MN-major: atoms along M/N are one TMA box apart (LBO), 8-row atoms along time 1024 B apart (SBO)
+            const uint64_t ad = make_smem_desc(sA + k * 2048, AT_BOX_BYTES, 1024);
+            const uint64_t bd = make_smem_desc(sB + k * 2048, AT_BOX_BYTES, 1024);
+            mma_f16_ss(tmem_base, ad, bd, idesc, (tb | pc | k) != 0);
+          }
+        }
+        mma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tfull);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int n = mt * TC_BM + q * 32 + lane;
+    float* out = p.partial + (size_t)sp * p.K * p.N;
+    if (n_tb > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+      uint32_t r[16];
+      if (n_tb > 0) {
+        tmem_ld_x16(taddr + c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      if (n < p.N) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = k_base + c0 + j;
+          if (k < p.K) out[(size_t)k * p.N + n] = __uint_as_float(r[j]);   // lanes = consecutive neurons: coalesced
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// posterior [T,K] fp32 -> two fp16 pieces [2][T][ld16] (hi + lo), zero padded
+__global__ void split_f16_kernel(int64_t T, int K, const float* __restrict__ src, int64_t lds,
+                                 __half* __restrict__ dst, int64_t ld16) {
+  const int64_t total = T * ld16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / ld16;
+    const int k = (int)(i - t * ld16);
+    const float v = k < K ? src[(size_t)t * lds + k] : 0.f;
+    const __half h = __float2half_rn(v);
+    dst[i] = h;
+    dst[total + i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+__global__ void split_reduce_kernel_tc(int splits, int64_t MN, const float* __restrict__ partial,
+                                       float* __restrict__ C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += (double)partial[(size_t)z * MN + i];
+  C[i] = (float)s;
+}
+
+static void atb_tc_plan(int64_t T, int K, int N, int& BN, int& n_mtiles, int& n_ntiles, int& splits,
+                        int64_t& t_per_split) {
+  BN = K >= 256 ? 256 : (K + 63) / 64 * 64;
+  n_ntiles = (K + BN - 1) / BN;
+  n_mtiles = (N + TC_BM - 1) / TC_BM;
+  const int tiles = n_mtiles * n_ntiles;
+  splits = (148 + tiles - 1) / tiles;
+  const int64_t max_splits = (T + 4 * AT_BKT - 1) / (4 * AT_BKT);
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  t_per_split = ((T + splits - 1) / splits + AT_BKT - 1) / AT_BKT * AT_BKT;
+  splits = (int)((T + t_per_split - 1) / t_per_split);
+}
+
+}  // namespace pmg
+
+extern "C" int pmg_split_f16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16,
+                             pmg_stream_t stream) {
+  if (T <= 0 || K <= 0 || !src || !dst16 || lds < K || ld16 < K || (ld16 & 7)) return PMG_ERR_BAD_ARG;
+  pmg::split_f16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(T, K, src, lds, (__half*)dst16, ld16);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int64_t pmg_atb_f16_workspace_bytes(int64_t T, int K, int N) {
+  if (T <= 0 || K <= 0 || N <= 0) return 0;
+  int BN, nm, nn, splits; int64_t tps;
+  pmg::atb_tc_plan(T, K, N, BN, nm, nn, splits, tps);
+  return (int64_t)splits * K * N * (int64_t)sizeof(float);
+}
+
+extern "C" int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
+                           float* yw, void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
+  using namespace pmg;
+  if (T <= 0 || K <= 0 || N <= 0 || !g16 || !y16 || !yw) return PMG_ERR_BAD_ARG;
+  if (ldg < K || (ldg & 7) || ldy16 < N || (ldy16 & 7)) return PMG_ERR_BAD_ARG;
+  if (((uintptr_t)g16 & 15) || ((uintptr_t)y16 & 15)) return PMG_ERR_ALIGNMENT;
+  if ((int64_t)AT_PG * T > ((int64_t)1 << 31) - 256) return PMG_ERR_UNSUPPORTED_SHAPE;
+  AtbTcParams p;
+  atb_tc_plan(T, K, N, p.BN, p.n_mtiles, p.n_ntiles, p.splits, p.t_per_split);
+  if (!workspace || workspace_bytes < (int64_t)p.splits * K * N * (int64_t)sizeof(float)) return PMG_ERR_WORKSPACE;
+  p.T = T; p.K = K; p.N = N; p.partial = (float*)workspace;
+  const uint32_t stage_bytes = 2 * AT_BOX_BYTES + AT_PG * (p.BN / 64) * AT_BOX_BYTES;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(p.BN);
+
+  CUtensorMap tmY, tmG;
+  // inner (contiguous) dimension = neurons / latent bins, outer = time; box = 32 time rows x 64 columns
+  int rc = make_tmap_f16(&tmY, y16, (uint64_t)T, (uint64_t)ldy16, (uint64_t)ldy16, AT_BKT);
+  if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+  rc = make_tmap_f16(&tmG, g16, (uint64_t)AT_PG * T, (uint64_t)ldg, (uint64_t)ldg, AT_BKT);
+  if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p.n_mtiles, p.n_ntiles, p.splits);
+  atb_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmY, tmG, p);
+  PMG_LAUNCH_CHECK();
+  const int64_t MN = (int64_t)K * N;
+  split_reduce_kernel_tc<<<cdiv(MN, 256), 256, 0, st>>>(p.splits, MN, p.partial, yw);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+// legacy hooks of pmg_atb (fp32 operands): the tensor-core path needs fp16 pieces, see pmg_atb_f16
 int64_t pmg_atb_tc_workspace_bytes(int64_t, int, int) { return 0; }
 int pmg_atb_tc_launch(int64_t, int, int, const float*, int64_t, const float*, int64_t, float*, int64_t, void*,
                       int64_t, cudaStream_t) {

@@ -10,6 +10,8 @@
 // the transition (a banded K x K operator, Toeplitz for the default RBF kernel)
 // is applied through a shared-memory exchange of the message, the rank-1 "jump"
 // part through a group reduction that is fused with the normaliser.
+#include <cuda_fp16.h>
+
 #include "pmg_common.cuh"
 
 namespace pmg {
@@ -49,6 +51,8 @@ struct BwdParams {
   const float* beta_in;
   float* gamma;
   float* gamma_lat;
+  __half* gamma16;       // [2][T][ldg]: fp16 hi/lo pieces of gamma_lat for the tensor-core statistics GEMM
+  int64_t ldg;
   float* dyn_marg;
   float* r_out;
   float* tw_partial;
@@ -529,6 +533,12 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
           const float g0 = ac0[q] * be0[q], g1 = ac1[q] * be1[q];
           if (g) { g[x] = g0; g[K + x] = g1; }
           if (gl_) gl_[x] = g0 + g1;
+          if (p.gamma16) {
+            const float gs = g0 + g1;
+            const __half h = __float2half_rn(gs);
+            p.gamma16[(size_t)t * p.ldg + x] = h;
+            p.gamma16[((size_t)c.T + t) * p.ldg + x] = __float2half_rn(gs - __half2float(h));
+          }
           tw_acc[q] += g0 + g1;
         }
       }
@@ -697,7 +707,7 @@ extern "C" int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, 
 
 extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
                             const float* alpha, const float* beta_in, float* gamma, float* gamma_lat,
-                            float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo,
+                            void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo,
                             float* beta_end, int mode, const int* chain_ids, int n_ids,
                             pmg_stream_t stream) {
   pmg::BwdParams p;
@@ -705,7 +715,9 @@ extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr,
   if (rc) return rc;
   if (!alpha) return PMG_ERR_BAD_ARG;
   if (mode == 1 && !beta_end) return PMG_ERR_BAD_ARG;
+  if (gamma16 && (ldg < tr->K || (ldg & 7))) return PMG_ERR_BAD_ARG;
   p.alpha = alpha; p.beta_in = beta_in; p.gamma = gamma; p.gamma_lat = gamma_lat; p.dyn_marg = dyn_marg;
+  p.gamma16 = (__half*)gamma16; p.ldg = ldg;
   p.r_out = r_out; p.tw_partial = tw_partial; p.beta_halo = beta_halo; p.beta_end = beta_end;
   const int n_groups = mode == 1 ? n_ids : plan->n_chain;
   return pmg::dispatch<false>(p, n_groups, (cudaStream_t)stream);

@@ -98,8 +98,9 @@ class EStep:
         torch.cuda.current_stream().synchronize()
         return self.err_host
 
-    def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False):
-        """One E-step.  Returns an EStepResult whose tensors alias this object's buffers."""
+    def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None):
+        """One E-step.  Returns an EStepResult whose tensors alias this object's buffers.
+        gamma16: optional [2,T,ldg] fp16 buffer that receives the hi/lo pieces of the latent posterior."""
         S = self.plan.n_chain
         K = self.K
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -113,7 +114,7 @@ class EStep:
         def bwd(mode=0, ids=None):
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
-                         mode=mode, chain_ids=ids)
+                         mode=mode, chain_ids=ids, gamma16=gamma16)
 
         ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=self.halo_state)
         n_relay_f = n_relay_b = 0

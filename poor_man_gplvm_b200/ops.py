@@ -219,12 +219,13 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
 
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
-             beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None):
+             beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None):
     lib = _lib.load()
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     check(lib.pmg_backward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(alpha), _p(beta_in), _p(gamma),
-                           _p(gamma_lat), _p(dyn_marg), _p(r_out), _p(tw_partial), _p(beta_halo), _p(beta_end),
+                           _p(gamma_lat), _p(gamma16), (gamma16.shape[2] if gamma16 is not None else 0), _p(dyn_marg),
+                           _p(r_out), _p(tw_partial), _p(beta_halo), _p(beta_end),
                            int(mode), _p(chain_ids), n_ids, _stream()), "pmg_backward")
     _count(1)
 
@@ -265,6 +266,40 @@ def atb(A, B, out=None, impl=0):
     ws = _workspace(nbytes, A.device)
     check(lib.pmg_atb(T, M, N, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), N, _p(ws), ws.numel(), int(impl),
                       _stream()), "pmg_atb")
+    _count(2)
+    return out
+
+
+def new_gamma16(T, K, device):
+    """[2, T, ldg] fp16 buffer for the hi/lo pieces of the posterior (padding columns zero)."""
+    ldg = (K + 7) // 8 * 8
+    return torch.zeros((2, T, ldg), dtype=torch.float16, device=device)
+
+
+def split_f16(src, out=None):
+    """fp32 [T,K] -> fp16 hi/lo pieces [2,T,ldg]."""
+    lib = _lib.load()
+    _f32(src, "src", 2)
+    T, K = src.shape
+    if out is None:
+        out = new_gamma16(T, K, src.device)
+    check(lib.pmg_split_f16(T, K, _p(src), K, _p(out), out.shape[2], _stream()), "pmg_split_f16")
+    _count(1)
+    return out
+
+
+def atb_f16(g16, y16, K, out=None):
+    """yw[K,N] = sum_t gamma[t,:K]^T y[t,:N] on the tensor cores (fp16 pieces, fp32 accumulation)."""
+    lib = _lib.load()
+    T, N = y16.T, y16.N
+    if g16.shape[1] != T:
+        raise ValueError("posterior pieces have %d bins, counts have %d" % (g16.shape[1], T))
+    if out is None:
+        out = torch.empty((K, N), dtype=torch.float32, device=g16.device)
+    nbytes = lib.pmg_atb_f16_workspace_bytes(T, K, N)
+    ws = _workspace(nbytes, g16.device)
+    check(lib.pmg_atb_f16(T, K, N, _p(g16), g16.shape[2], _p(y16.data), y16.ld, _p(out), _p(ws), ws.numel(),
+                          _stream()), "pmg_atb_f16")
     _count(2)
     return out
 

@@ -186,6 +186,23 @@ def test_atb_matches_numpy(ops, T, M, N, impl):
     assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 5e-6
 
 
+@pytest.mark.parametrize("T,K,N", [(1, 3, 5), (1000, 100, 30), (4099, 130, 70), (20000, 400, 500), (3000, 600, 200)])
+def test_atb_f16_tensor_core_matches_numpy(ops, T, K, N):
+    """Statistics GEMM on tcgen05: posterior as fp16 hi/lo pieces (22 bits), counts exact in fp16."""
+    rng = np.random.default_rng(T + K)
+    G = rng.random((T, K)).astype(np.float32) ** 6
+    G /= G.sum(axis=1, keepdims=True)
+    Y = rng.poisson(0.7, size=(T, N)).astype(np.float32)
+    want = G.astype(np.float64).T @ Y.astype(np.float64)
+    y16 = ops.CountsF16(dev(Y))
+    g16 = ops.split_f16(dev(G))
+    got = host(ops.atb_f16(g16, y16, K))
+    # fp16 pieces: per-element error <= max(2^-22 rel, 3e-8 abs); sums of T terms
+    assert np.max(np.abs(got - want)) < 2e-6 * np.max(np.abs(want)) + 1e-5
+    ref32 = host(ops.atb(dev(G), dev(Y), impl=1))
+    assert np.max(np.abs(got - ref32)) < 4e-6 * np.max(np.abs(want)) + 1e-5
+
+
 # ----------------------------------------------------------------------------- M-step
 @pytest.mark.parametrize("K,N,ls", [(30, 7, 5.0), (100, 30, 10.0), (100, 33, 1.0), (400, 50, 10.0)])
 def test_mstep_adam_matches_oracle(ops, K, N, ls):
