@@ -109,9 +109,14 @@ typedef struct pmg_scan_plan {
  * mode 1: relay — run only chains listed in chain_ids[n_ids] (device int32) starting
  *         from the exact carry alpha[t_begin-1].
  * alpha:   [T, 2, K] (ld = 2*ldk), lmr: [T] = log c_t + s*max_k ll[t,k]
- * carry_in: [2,K] or NULL (uniform);   halo_state: [n_chain, 2, K] warmed-up state at t_begin-1. */
+ * carry_in: [2,K] or NULL (uniform);   halo_state: [n_chain, 2, K] warmed-up state at t_begin-1.
+ * warm_in:  message a warm-up starts from: one [2,K] vector (warm_stride 0, e.g. the stationary
+ *           distribution of the prior chain) or one per chain (warm_stride 2K: the previous EM
+ *           iteration's message at that bin); NULL = uniform.  warm_out: [n_chain,2,K] or NULL,
+ *           receives the message at each chain's warm-up start for the next pass. */
 int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
-                const float* carry_in, float* alpha, float* lmr, float* halo_state, int mode,
+                const float* carry_in, const float* warm_in, int64_t warm_stride, float* warm_out,
+                float* alpha, float* lmr, float* halo_state, int mode,
                 const int* chain_ids, int n_ids, pmg_stream_t stream);
 
 /* gamma:      [T, 2, K] or NULL; gamma_lat: [T, K] or NULL (sum over dynamics); dyn_marg: [T,2] or NULL
@@ -121,7 +126,8 @@ int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, const float
  * tw_partial: [n_chain, K] or NULL (per-chain sum_t gamma_lat)
  * beta_in:    [2,K] or NULL (ones);  beta_halo / beta_end: [n_chain, 2, K]. */
 int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
-                 const float* alpha, const float* beta_in, float* gamma, float* gamma_lat,
+                 const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
+                 float* warm_out, float* gamma, float* gamma_lat,
                  void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo, float* beta_end,
                  int mode, const int* chain_ids, int n_ids, pmg_stream_t stream);
 

@@ -218,8 +218,8 @@ class PoissonGPLVMJump1D:
         pjm = hyperparam.get('p_jump_to_move', self.p_jump_to_move)
         P, logP, M, logM = gpk.create_transition_prob_1d(self.possible_latent_bin, self.possible_dynamics, mv, pmj, pjm,
                                                          custom_kernel=self.custom_transition_kernel)
-        host = gpk.move_operator_host(self.n_latent_bin, mv, self.custom_transition_kernel)
-        op = ops.MoveOperator(host, M, self.device)
+        host = gpk.move_operator_host(self.n_latent_bin, mv, self.custom_transition_kernel, p_move_to_jump=pmj)
+        op = ops.MoveOperator(host, M, self.device, P0=P[0])
         return P, logP, M, logM, op
 
     def _masks(self, ma_neuron, ma_latent, T):

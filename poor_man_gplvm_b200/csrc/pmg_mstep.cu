@@ -188,14 +188,21 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mstep_adam_kernel(const MstepPa
     }
   };
   auto gather = [&](int slot, float& loss, float& err) {
-    if (tid == 0) {
+    if (tid < 32) {
+      // one warp, fixed order (lane-strided partial sums, then a butterfly): every CTA computes the
+      // same bits, so all CTAs take the same stop decision
       double s0 = 0.0, s1 = 0.0;
-      for (unsigned c = 0; c < gridDim.x; ++c) {
-        s0 += p.partials[((size_t)slot * gridDim.x + c) * 2 + 0];
-        s1 += p.partials[((size_t)slot * gridDim.x + c) * 2 + 1];
+      const double* src = p.partials + (size_t)slot * gridDim.x * 2;
+      for (unsigned c = tid; c < gridDim.x; c += 32) {
+        s0 += __ldcg(src + 2 * c);
+        s1 += __ldcg(src + 2 * c + 1);
       }
-      bcast[0] = (float)s0;
-      bcast[1] = sqrtf((float)s1);
+      s0 = warp_sum_d(s0);
+      s1 = warp_sum_d(s1);
+      if (tid == 0) {
+        bcast[0] = (float)s0;
+        bcast[1] = sqrtf((float)s1);
+      }
     }
     __syncthreads();
     loss = bcast[0]; err = bcast[1];

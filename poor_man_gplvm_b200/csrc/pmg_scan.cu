@@ -40,6 +40,9 @@ struct ScanCommon {
 struct FwdParams {
   ScanCommon c;
   const float* carry_in;
+  const float* warm_in;     // initial message of approximate (warm-up) starts: [2K] (stride 0) or per chain
+  int64_t warm_stride;
+  float* warm_out;          // [n_chain][2K]: message at the next chain's warm-up start (for the next pass)
   float* alpha;
   float* lmr;
   float* halo_state;
@@ -49,6 +52,9 @@ struct BwdParams {
   ScanCommon c;
   const float* alpha;
   const float* beta_in;
+  const float* warm_in;
+  int64_t warm_stride;
+  float* warm_out;
   float* gamma;
   float* gamma_lat;
   __half* gamma16;       // [2][T][ldg]: fp16 hi/lo pieces of gamma_lat for the tensor-core statistics GEMM
@@ -257,13 +263,17 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
   const float* src = nullptr;
   if (c.mode == 1) {
     t0 = cr.t_begin;
-    if (t0 > 0) { from_array = true; src = p.alpha + (size_t)(t0 - 1) * 2 * K; }
+    if (p.warm_in) { from_array = true; src = p.warm_in + (size_t)cr.s * p.warm_stride; }   // snapshot of the carry
+    else if (t0 > 0) { from_array = true; src = p.alpha + (size_t)(t0 - 1) * 2 * K; }
     else if (p.carry_in) { from_array = true; src = p.carry_in; }
   } else {
     t0 = cr.t_begin - c.halo;
-    if (t0 <= 0) {
+    if (t0 <= 0 && c.left_exact) {
       t0 = 0;
-      if (c.left_exact && p.carry_in) { from_array = true; src = p.carry_in; }
+      if (p.carry_in) { from_array = true; src = p.carry_in; }
+    } else {
+      if (t0 < 0) t0 = 0;
+      if (p.warm_in) { from_array = true; src = p.warm_in + (size_t)cr.s * p.warm_stride; }
     }
   }
   float p1;
@@ -360,6 +370,17 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
         }
       }
     }
+    if (p.warm_out && t == cr.t_end - c.halo - 1 && cr.s + 1 < c.n_chain) {
+      float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        if (valid[q]) {
+          const int x = own_x<Q, WPC, WT>(gl, q);
+          o[x] = al0[q];
+          o[K + x] = al1[q];
+        }
+      }
+    }
   }
 }
 
@@ -417,13 +438,18 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
   int64_t t_hi;
   const float* init = nullptr;
   if (c.mode == 1) {
-    if (cr.t_end < c.T) { t_hi = cr.t_end; init = p.beta_end + (size_t)(cr.s + 1) * 2 * K; }
-    else { t_hi = c.T - 1; init = p.beta_in; }
+    if (cr.t_end < c.T) {
+      t_hi = cr.t_end;
+      init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
+    } else { t_hi = c.T - 1; init = p.beta_in; }
   } else {
     t_hi = cr.t_end - 1 + c.halo;
-    if (t_hi >= c.T - 1) {
+    if (t_hi >= c.T - 1 && c.right_exact) {
       t_hi = c.T - 1;
-      if (c.right_exact) init = p.beta_in;
+      init = p.beta_in;
+    } else {
+      if (t_hi > c.T - 1) t_hi = c.T - 1;
+      if (p.warm_in) init = p.warm_in + (size_t)cr.s * p.warm_stride;
     }
   }
 
@@ -579,6 +605,17 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
         }
       }
     }
+    if (p.warm_out && t == cr.t_begin + c.halo - 1 && cr.s >= 1) {
+      float* o = p.warm_out + (size_t)(cr.s - 1) * 2 * K;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        if (valid[q]) {
+          const int x = own_x<Q, WPC, WT>(gl, q);
+          o[x] = be0[q];
+          o[K + x] = be1[q];
+        }
+      }
+    }
   }
   if (p.tw_partial) {
     float* o = p.tw_partial + (size_t)cr.s * K;
@@ -641,13 +678,48 @@ static int launch_bwd(const BwdParams& p, int n_groups, cudaStream_t st) {
 
 constexpr int kRegWT = 10;   // compile-time half width of the register-window Toeplitz path
 
+}  // namespace pmg
+#include "pmg_scan_bulk.cuh"
+#include <cstdlib>
+namespace pmg {
+
+static bool bulk_ok(const FwdParams& p) {
+  return (((uintptr_t)p.c.ll | (uintptr_t)p.alpha) & 15) == 0;
+}
+static bool bulk_ok(const BwdParams& p) {
+  return (((uintptr_t)p.c.ll | (uintptr_t)p.alpha | (uintptr_t)p.gamma16) & 15) == 0;
+}
+
 // choose (Q, WPC): smallest group that covers K with at most 16 bins per thread
 template <bool FWD, typename P>
 static int dispatch(const P& p, int n_groups, cudaStream_t st) {
   const int K = p.c.tr.K;
   const bool reg = p.c.tr.kind == 0 && p.c.tr.W <= kRegWT;
+  // whole-row bulk copies need 16-byte rows: K % 8 == 0 (fp16 posterior pieces), ld % 4 == 0
+  static const bool direct_only = std::getenv("PMG_SCAN_DIRECT") != nullptr;
+  // warps (= chains) per CTA of the bulk kernels: 16 (one staging buffer, <= 128 registers) or 8 (two buffers)
+  static const int nw_fwd = std::getenv("PMG_SCAN_NW_FWD") ? std::atoi(std::getenv("PMG_SCAN_NW_FWD")) : 16;
+  static const int nw_bwd = std::getenv("PMG_SCAN_NW_BWD") ? std::atoi(std::getenv("PMG_SCAN_NW_BWD")) : 8;
+  const bool nw16 = (FWD ? nw_fwd : nw_bwd) == 16;
+  const bool w5 = p.c.tr.W <= 5;
+  const bool bulk = reg && !direct_only && (K % 8 == 0) && (p.c.ldll % 4 == 0) && bulk_ok(p) && p.c.scale > 0.f;
 #define PMG_CASE(Qv, WPCv)                                                                     \
   do {                                                                                         \
+    if (bulk && WPCv == 1) {                                                                   \
+      int rc_;                                                                                 \
+      if constexpr (FWD) {                                                                     \
+        if (w5) rc_ = nw16 ? launch_fwd_bulk<Qv, 5, 16, 1>(p, n_groups, st)                    \
+                           : launch_fwd_bulk<Qv, 5, 8, 2>(p, n_groups, st);                    \
+        else rc_ = nw16 ? launch_fwd_bulk<Qv, 10, 16, 1>(p, n_groups, st)                      \
+                        : launch_fwd_bulk<Qv, 10, 8, 2>(p, n_groups, st);                      \
+      } else {                                                                                 \
+        if (w5) rc_ = nw16 ? launch_bwd_bulk<Qv, 5, 16, 1>(p, n_groups, st)                    \
+                           : launch_bwd_bulk<Qv, 5, 8, 2>(p, n_groups, st);                    \
+        else rc_ = nw16 ? launch_bwd_bulk<Qv, 10, 16, 1>(p, n_groups, st)                      \
+                        : launch_bwd_bulk<Qv, 10, 8, 2>(p, n_groups, st);                      \
+      }                                                                                        \
+      if (rc_ != PMG_ERR_UNSUPPORTED_SHAPE) return rc_;                                        \
+    }                                                                                          \
     if (reg) {                                                                                 \
       if constexpr (FWD) return launch_fwd<Qv, WPCv, kRegWT>(p, n_groups, st);                 \
       else return launch_bwd<Qv, WPCv, kRegWT>(p, n_groups, st);                               \
@@ -694,19 +766,21 @@ static int fill_common(ScanCommon& c, const pmg_scan_plan* plan, const pmg_trans
 }  // namespace pmg
 
 extern "C" int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
-                           const float* carry_in, float* alpha, float* lmr, float* halo_state, int mode,
+                           const float* carry_in, const float* warm_in, int64_t warm_stride, float* warm_out,
+                           float* alpha, float* lmr, float* halo_state, int mode,
                            const int* chain_ids, int n_ids, pmg_stream_t stream) {
   pmg::FwdParams p;
   int rc = pmg::fill_common(p.c, plan, tr, ll, ldll, mode, chain_ids, n_ids);
   if (rc) return rc;
   if (!alpha || !lmr) return PMG_ERR_BAD_ARG;
-  p.carry_in = carry_in; p.alpha = alpha; p.lmr = lmr; p.halo_state = halo_state;
+  p.carry_in = carry_in; p.warm_in = warm_in; p.warm_stride = warm_stride; p.warm_out = warm_out; p.alpha = alpha; p.lmr = lmr; p.halo_state = halo_state;
   const int n_groups = mode == 1 ? n_ids : plan->n_chain;
   return pmg::dispatch<true>(p, n_groups, (cudaStream_t)stream);
 }
 
 extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
-                            const float* alpha, const float* beta_in, float* gamma, float* gamma_lat,
+                            const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
+                            float* warm_out, float* gamma, float* gamma_lat,
                             void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo,
                             float* beta_end, int mode, const int* chain_ids, int n_ids,
                             pmg_stream_t stream) {
@@ -714,9 +788,10 @@ extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr,
   int rc = pmg::fill_common(p.c, plan, tr, ll, ldll, mode, chain_ids, n_ids);
   if (rc) return rc;
   if (!alpha) return PMG_ERR_BAD_ARG;
-  if (mode == 1 && !beta_end) return PMG_ERR_BAD_ARG;
+  if (mode == 1 && !beta_end && !warm_in) return PMG_ERR_BAD_ARG;
   if (gamma16 && (ldg < tr->K || (ldg & 7))) return PMG_ERR_BAD_ARG;
-  p.alpha = alpha; p.beta_in = beta_in; p.gamma = gamma; p.gamma_lat = gamma_lat; p.dyn_marg = dyn_marg;
+  p.alpha = alpha; p.beta_in = beta_in; p.warm_in = warm_in; p.warm_stride = warm_stride; p.warm_out = warm_out;
+  p.gamma = gamma; p.gamma_lat = gamma_lat; p.dyn_marg = dyn_marg;
   p.gamma16 = (__half*)gamma16; p.ldg = ldg;
   p.r_out = r_out; p.tw_partial = tw_partial; p.beta_halo = beta_halo; p.beta_end = beta_end;
   const int n_groups = mode == 1 ? n_ids : plan->n_chain;

@@ -69,6 +69,13 @@ class EStep:
         self.beta_halo = torch.zeros((S, 2, self.K), **f32)
         self.beta_end = torch.zeros((S, 2, self.K), **f32)
         self.tw_partial = torch.zeros((S, self.K), **f32)
+        # warm-up starts: ping-pong buffers holding, for every chain, the message of the previous pass
+        # at the bin where its warm-up starts (forward and backward); before the first pass the forward
+        # warm-up starts from the stationary distribution of the prior chain (exact for flat likelihoods)
+        self.fwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
+        self.bwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
+        self.warm_cur = 0
+        self.warm_valid = False
         self.err = torch.zeros(2 * max(S, 1), **f32)
         self.err_host = torch.zeros(2 * max(S, 1), dtype=torch.float32).pin_memory()
 
@@ -111,12 +118,18 @@ class EStep:
         dyn = torch.empty((self.T, 2), **f32) if want_dyn else None
         r = torch.zeros((self.T, 2, K), **f32) if want_r else None
 
-        def bwd(mode=0, ids=None):
+        cur, nxt = self.warm_cur, 1 - self.warm_cur
+        f_in = self.fwarm[cur] if self.warm_valid else getattr(self.op, "stationary", None)
+        b_in = self.bwarm[cur] if self.warm_valid else None
+
+        def bwd(mode=0, ids=None, carry=None):
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
-                         mode=mode, chain_ids=ids, gamma16=gamma16)
+                         mode=mode, chain_ids=ids, gamma16=gamma16, warm_in=(b_in if mode == 0 else carry),
+                         warm_out=self.bwarm[nxt])
 
-        ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=self.halo_state)
+        ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=self.halo_state, warm_in=f_in,
+                    warm_out=self.fwarm[nxt])
         n_relay_f = n_relay_b = 0
         if S > 1:
             self._check_fwd(S - 1)
@@ -128,40 +141,44 @@ class EStep:
             err = self._read_err()
             ef = err[1:S].clone()            # ef[c-1]: seam in front of chain c
             eb = err[S:2 * S - 1].clone()    # eb[c]:   seam behind chain c
-            bad = set((torch.nonzero(ef > self.seam_tol).flatten() + 1).tolist())
-            if bad:
-                # relay the exact carry: only the head of each run of consecutive failing
-                # chains can start (its predecessor is final); the rest wait for the next round
-                while bad:
-                    heads = sorted(c for c in bad if (c - 1) not in bad)
-                    n_relay_f += len(heads)
-                    ids = torch.tensor(heads, dtype=torch.int32, device=self.dev)
-                    ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=None, mode=1,
-                                chain_ids=ids)
-                    bad.difference_update(heads)
-                    recheck = [c + 1 for c in heads if c + 1 < S and (c + 1) not in bad]
-                    if recheck:
-                        self._check_fwd(S - 1)
-                        e2 = self._read_err()[1:S]
-                        bad.update(c for c in recheck if float(e2[c - 1]) > self.seam_tol)
+            # Seam repair = parallel (Jacobi) sweeps: every chain whose incoming message was off restarts,
+            # all at once, from a snapshot of its neighbour's current boundary message; the seams are then
+            # re-verified against the messages those restarts produced.  Each sweep extends the effective
+            # warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length (in the worst,
+            # non-mixing case it degenerates to the reference's sequential walk).
+            rows = torch.arange(1, S, device=self.dev) * self.chunk_len - 1      # bin t_begin(c)-1, c = 1..S-1
+            redo_bwd = False
+            for _ in range(S):
+                bad = torch.nonzero(ef > self.seam_tol).flatten() + 1
+                if not bad.numel():
+                    break
+                redo_bwd = True
+                n_relay_f += int(bad.numel())
+                ids = bad.to(device=self.dev, dtype=torch.int32)
+                self.halo_state[ids.long()] = self.alpha[rows[ids.long() - 1]]   # carry snapshot = new "estimate"
+                ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=None, mode=1,
+                            chain_ids=ids, warm_in=self.halo_state, warm_out=self.fwarm[nxt])
+                self._check_fwd(S - 1)
+                ef = self._read_err()[1:S].clone()
+            if redo_bwd:
                 bwd()
                 self._check_bwd(S - 1)
                 eb = self._read_err()[S:2 * S - 1].clone()
-            bad = set(torch.nonzero(eb > self.seam_tol).flatten().tolist())
-            while bad:
-                heads = sorted(c for c in bad if (c + 1) not in bad)
-                n_relay_b += len(heads)
-                ids = torch.tensor(heads, dtype=torch.int32, device=self.dev)
-                bwd(mode=1, ids=ids)
-                bad.difference_update(heads)
-                recheck = [c - 1 for c in heads if c - 1 >= 0 and (c - 1) not in bad]
-                if recheck:
-                    self._check_bwd(S - 1)
-                    e2 = self._read_err()[S:2 * S - 1]
-                    bad.update(c for c in recheck if float(e2[c]) > self.seam_tol)
+            for _ in range(S):
+                bad = torch.nonzero(eb > self.seam_tol).flatten()
+                if not bad.numel():
+                    break
+                n_relay_b += int(bad.numel())
+                ids = bad.to(device=self.dev, dtype=torch.int32)
+                self.beta_halo[ids.long()] = self.beta_end[ids.long() + 1]
+                bwd(mode=1, ids=ids, carry=self.beta_halo)
+                self._check_bwd(S - 1)
+                eb = self._read_err()[S:2 * S - 1].clone()
         else:
             ef = eb = torch.zeros(0)
 
+        if S > 1:
+            self.warm_cur, self.warm_valid = nxt, True
         res = EStepResult()
         res.ll, res.alpha, res.lmr = self.ll, self.alpha, self.lmr
         res.gamma, res.gamma_lat, res.dyn_marg, res.r = gamma, gamma_lat, dyn, r

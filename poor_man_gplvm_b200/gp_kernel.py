@@ -70,7 +70,19 @@ def generate_basis(lengthscale, n_latent_bin, explained_variance_threshold_basis
     return np.ascontiguousarray(basis, dtype=np.float32)
 
 
-def move_operator_host(n_latent_bin, movement_variance=1., custom_kernel=None):
+def tap_floor(n_latent_bin, p_move_to_jump):
+    """Entries of the move kernel below this value (relative to its diagonal) are treated as zero.
+
+    Every joint transition row carries at least p_move_to_jump/K of mass on every (jump, x') state,
+    so a move-kernel entry below 1e-6 of that floor perturbs no posterior entry by more than fp32
+    rounding; the floor is additionally capped at 1e-11.  With p_move_to_jump == 0 nothing is
+    dropped above the fp32 normal range."""
+    if p_move_to_jump is None or p_move_to_jump <= 0:
+        return _TAP_FLOOR
+    return max(_TAP_FLOOR, min(1e-11, 1e-6 * float(p_move_to_jump) / float(n_latent_bin)))
+
+
+def move_operator_host(n_latent_bin, movement_variance=1., custom_kernel=None, p_move_to_jump=None):
     """Factor the "move" transition P0 for the scan kernels.
 
     Default RBF kernel: P0[x,x'] = taps[|x-x'|] * inv_z[x] (Toeplitz numerator, row
@@ -84,13 +96,13 @@ def move_operator_host(n_latent_bin, movement_variance=1., custom_kernel=None):
         taps_full = np.exp(-(d ** 2) / np.float32(movement_variance) ** 2).astype(np.float32)
         lin0, _ = rbf_kernel_matrix(K, movement_variance, 1.0)
         z = lin0.sum(axis=1)
-        nz = np.nonzero(taps_full >= _TAP_FLOOR)[0]
+        nz = np.nonzero(taps_full >= tap_floor(K, p_move_to_jump))[0]
         W = int(nz.max()) if nz.size else 0
         return {"kind": 0, "W": W, "taps": np.ascontiguousarray(taps_full[:W + 1]),
                 "inv_z": (np.float32(1.0) / z).astype(np.float32)}
     lin0 = np.asarray(custom_kernel, dtype=np.float32)
     P0 = lin0 / lin0.sum(axis=1, keepdims=True)
-    ii, jj = np.nonzero(P0 >= _TAP_FLOOR)
+    ii, jj = np.nonzero(P0 >= tap_floor(K, p_move_to_jump) * max(float(P0.max()), 1e-30))
     W = int(np.abs(ii - jj).max()) if ii.size else 0
     band_fwd = np.zeros((2 * W + 1, K), dtype=np.float32)
     band_bwd = np.zeros((2 * W + 1, K), dtype=np.float32)

@@ -173,10 +173,34 @@ def naive_bayes_normalize(ll, inplace=False):
 
 
 # ----------------------------------------------------------------------------- transitions
+def stationary_joint(P0, M):
+    """Stationary distribution pi[2,K] of T[(d,x),(d',x')] = M[d,d'] P_{d'}[x,x'] with P_1 = 1/K.
+    The jump component is uniform, pi_1 = pi_d(1)/K; the move component solves
+    pi_0 (I - M00 P0) = M10 pi_1 P0."""
+    K = P0.shape[0]
+    M = np.asarray(M, dtype=np.float64)
+    pmj, pjm = M[0, 1], M[1, 0]
+    if pmj + pjm <= 0:
+        return np.full((2, K), 0.5 / K, dtype=np.float32)
+    pd1 = pmj / (pmj + pjm)
+    pi1 = np.full(K, pd1 / K)
+    rhs = M[1, 0] * (pi1 @ P0)
+    A = np.eye(K) - M[0, 0] * P0
+    try:
+        pi0 = np.linalg.solve(A.T, rhs)
+    except np.linalg.LinAlgError:
+        return np.full((2, K), 0.5 / K, dtype=np.float32)
+    pi = np.stack([np.maximum(pi0, 0), pi1])
+    return (pi / pi.sum()).astype(np.float32)
+
+
 class MoveOperator:
     """Device copy of the factored "move" transition + the 2x2 dynamics matrix."""
 
-    def __init__(self, host, M, device):
+    def __init__(self, host, M, device, P0=None):
+        """P0: optional dense row-normalised move matrix [K,K] (host); when given, the stationary
+        distribution of the joint (dynamics x latent) prior chain is computed and used as the
+        message that time-parallel warm-ups start from."""
         self.K = int(host["inv_z"].shape[0]) if host["kind"] == 0 else int(host["band_fwd"].shape[1])
         self.kind, self.W = int(host["kind"]), int(host["W"])
         self.M = np.asarray(M, dtype=np.float32).reshape(4)
@@ -185,6 +209,9 @@ class MoveOperator:
         self.inv_z = dev(host["inv_z"]) if self.kind == 0 else None
         self.band_fwd = dev(host["band_fwd"]) if self.kind == 1 else None
         self.band_bwd = dev(host["band_bwd"]) if self.kind == 1 else None
+        self.stationary = None
+        if P0 is not None:
+            self.stationary = dev(stationary_joint(np.asarray(P0, dtype=np.float64), self.M.reshape(2, 2)))
 
     def cstruct(self):
         s = PmgTransition()
@@ -209,21 +236,34 @@ def make_plan(T, core_begin, core_end, chunk_len, halo, left_exact, right_exact,
     return p
 
 
-def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None):
+def _warm(warm_in):
+    """(pointer, stride): one [2,K] vector shared by all chains, or [n_chain,2,K] with one per chain."""
+    if warm_in is None:
+        return None, 0
+    return _p(warm_in), (0 if warm_in.dim() == 2 else warm_in.stride(0))
+
+
+def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None, warm_in=None,
+            warm_out=None):
     lib = _lib.load()
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
-    check(lib.pmg_forward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(carry_in), _p(alpha), _p(lmr),
+    wp, ws = _warm(warm_in)
+    check(lib.pmg_forward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(carry_in), wp, ws, _p(warm_out),
+                          _p(alpha), _p(lmr),
                           _p(halo_state), int(mode), _p(chain_ids), n_ids, _stream()), "pmg_forward")
     _count(1)
 
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
-             beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None):
+             beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
+             warm_out=None):
     lib = _lib.load()
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
-    check(lib.pmg_backward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(alpha), _p(beta_in), _p(gamma),
+    wp, ws = _warm(warm_in)
+    check(lib.pmg_backward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(alpha), _p(beta_in), wp, ws,
+                           _p(warm_out), _p(gamma),
                            _p(gamma_lat), _p(gamma16), (gamma16.shape[2] if gamma16 is not None else 0), _p(dyn_marg),
                            _p(r_out), _p(tw_partial), _p(beta_halo), _p(beta_end),
                            int(mode), _p(chain_ids), n_ids, _stream()), "pmg_backward")

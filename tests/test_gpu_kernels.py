@@ -83,7 +83,8 @@ def test_naive_bayes_normalize(ops):
 def _transition(K, mv, custom=None, pmj=0.02, pjm=0.05):
     from poor_man_gplvm_b200 import gp_kernel as gpk
     P, logP, M, logM = gpk.create_transition_prob_1d(np.arange(K), np.arange(2), mv, pmj, pjm, custom_kernel=custom)
-    hostop = gpk.move_operator_host(K, mv, custom)
+    # band truncation against the jump floor (W=5 at movement_variance=1); K=200 keeps the full fp32 support (W=9)
+    hostop = gpk.move_operator_host(K, mv, custom, p_move_to_jump=None if K == 200 else pmj)
     return P, logP, M, logM, hostop
 
 
@@ -105,6 +106,9 @@ SCAN_CASES = [
     (200, 1.0, None, 600, 128, 64),      # Q=8 reg
     (400, 1.0, None, 500, 125, 96),      # Q=13 reg
     (500, 0.7, None, 260, 90, 64),       # Q=16 reg
+    (96, 1.0, None, 400, 100, 64),       # Q=4, bulk-copy kernels (K % 8 == 0)
+    (512, 1.0, None, 300, 100, 64),      # Q=16, bulk-copy kernels
+    (400, 1.0, None, 3000, 256, 128),    # Q=13 bulk, many ring wraps
     (100, 3.0, None, 700, 175, 128),     # Toeplitz generic path (W=27)
     (600, 1.0, None, 150, 50, 40),       # WPC=2
     (1100, 1.0, None, 100, 100, 0),      # WPC=4
