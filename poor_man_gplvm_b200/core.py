@@ -14,8 +14,10 @@ import numpy as np
 import torch
 
 from . import gp_kernel as gpk
+from . import hostio
 from . import ops
 from .estep import EStep
+from .shard import TimeShard
 
 
 def _unwrap_tsd(y):
@@ -72,14 +74,15 @@ class EMLoop:
     ``fit_em``: statistics -> Adam M-step -> tuning -> E-step."""
 
     def __init__(self, model, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
-                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None):
+                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None, shard=None):
         self.y = y_dev
         self.Phi = model._dev(tuning_basis)
         self.W = model._dev(model.params).clone()
         if self.W.shape != (self.Phi.shape[1], model.n_neuron):
             raise ValueError("params shape %s does not match basis %s" % (tuple(self.W.shape), tuple(self.Phi.shape)))
         self.state = ops.AdamState(self.W)
-        self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len)
+        self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len, shard=shard)
+        self.shard = self.es.shard
         gamma_lat = torch.exp(model._dev(log_posterior_init))
         if gamma_lat.shape != (y_dev.shape[0], op.K):
             raise ValueError("log_posterior_init must be [T, n_latent_bin]")
@@ -88,7 +91,10 @@ class EMLoop:
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
         self.use_tc = self.es.y16 is not None and self.es.y16.exact
         if self.use_tc:
-            self.gamma16 = ops.split_f16(gamma_lat)
+            # pieces live on the rank's extended block (core + neighbour halos); halo rows stay zero, so
+            # the time reduction over the extended block only counts this rank's own bins
+            self.gamma16 = ops.new_gamma16(self.es.T, op.K, y_dev.device)
+            self.gamma16[:, self.es.core] = ops.split_f16(gamma_lat)
             self.gamma_lat = None
         else:
             self.gamma16 = None
@@ -100,6 +106,7 @@ class EMLoop:
             yw = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)  # reference core.py:807
         else:
             yw = ops.atb(self.gamma_lat, self.y)
+        self.shard.allreduce_sum_(yw, self.tw)                      # time-sharded ranks: one packed all-reduce
         ops.phase("stats")
         m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
                                self.maxiter, self.tol)             # reference core.py:810
@@ -107,6 +114,10 @@ class EMLoop:
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16)
         self.gamma_lat, self.tw = res.gamma_lat, res.tw            # reference core.py:668
+        if self.shard.active:
+            lm = res.log_marginal.reshape(1)
+            self.shard.allreduce_sum_(lm)
+            res.log_marginal = lm[0]
         return res, m_res
 
 
@@ -183,7 +194,8 @@ class PoissonGPLVMJump1D:
 
     @staticmethod
     def _host(t):
-        return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        """device tensor -> NumPy (pinned, pipelined copy for the T-sized arrays)"""
+        return hostio.to_numpy(t) if isinstance(t, torch.Tensor) else np.asarray(t)
 
     # ------------------------------------------------------------------ reference API
     def get_tuning(self, params, hyperparam, tuning_basis):
@@ -233,6 +245,19 @@ class PoissonGPLVMJump1D:
         ma_l = np.asarray(self._host(ma_latent), dtype=np.float32)
         return self._dev(ma_n), self._dev(ma_l)
 
+    def _transition_counts(self, es, res, logP, logM):
+        """log sum_t xi_t (reference decoder.py:215-221) = log(M * P * (alpha^T r)): one time-reduction GEMM
+        over this rank's (t, t+1) pairs, summed over ranks, then the [2,2,K,K] epilogue."""
+        K = self.n_latent_bin
+        c = res.core
+        hi = c.stop - 1 if es.shard.is_last else c.stop          # pairs (t, t+1) with t in [c.start, hi)
+        if hi > c.start:
+            G = ops.atb(res.alpha_ext.view(-1, 2 * K)[c.start:hi], res.r_ext.view(-1, 2 * K)[c.start + 1:hi + 1])
+        else:
+            G = torch.zeros((2 * K, 2 * K), dtype=torch.float32, device=self.device)
+        es.shard.allreduce_sum_(G)
+        return ops.xi_finalize(G, self._dev(logP), logM)
+
     def _decode_latent(self, y, tuning, hyperparam, log_latent_transition_kernel_l=None,
                        log_dynamics_transition_kernel=None, ma_neuron=None, ma_latent=None, likelihood_scale=1.,
                        n_time_per_chunk=10000, return_device=False, _want_r=True):
@@ -249,9 +274,7 @@ class PoissonGPLVMJump1D:
         res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=False, want_dyn=False, want_r=_want_r)
         log_acc = None
         if _want_r and y_dev.shape[0] > 1:
-            T, K = y_dev.shape[0], self.n_latent_bin
-            G = ops.atb(res.alpha.view(T, 2 * K)[:T - 1], res.r.view(T, 2 * K)[1:])
-            log_acc = ops.xi_finalize(G, self._dev(logP), logM)
+            log_acc = self._transition_counts(es, res, logP, logM)
         out = (torch.log(res.gamma), res.log_marginal.to(torch.float32), torch.log(res.alpha), res.lmr, log_acc,
                res.ll)
         if return_device:
@@ -259,8 +282,10 @@ class PoissonGPLVMJump1D:
         return tuple(None if o is None else self._host(o) for o in out)
 
     def decode_latent(self, y, tuning=None, hyperparam={}, ma_neuron=None, ma_latent=None, likelihood_scale=1.,
-                      n_time_per_chunk=10000, t_l=None, return_device=False):
-        """reference core.py:454-497 (same keys)."""
+                      n_time_per_chunk=10000, t_l=None, return_device=False, time_sharded=False, group=None):
+        """reference core.py:454-497 (same keys).  time_sharded=True (under torch.distributed): ``y`` is this
+        rank's contiguous block of time bins; T-sized results cover that block, scalars and the transition
+        statistics are global."""
         y, t_in = _unwrap_tsd(y)
         if t_in is not None:
             t_l = t_in
@@ -270,21 +295,27 @@ class PoissonGPLVMJump1D:
         T, K = y_dev.shape[0], self.n_latent_bin
         P, logP, M, logM, op = self._transition_pack(hyperparam)
         ma_n, ma_l = self._masks(ma_neuron, ma_latent, T)
-        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale)
-        res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=True, want_dyn=True, want_r=T > 1)
+        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, shard=TimeShard(group) if time_sharded else None)
+        res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=True, want_dyn=True,
+                     want_r=(T > 1 or es.shard.active))
+        if es.shard.active:
+            lm = res.log_marginal.reshape(1)
+            es.shard.allreduce_sum_(lm)
+            res.log_marginal = lm[0]
         conv = (lambda t: t) if return_device else self._host
+        # the reference leaves these on the device as jax arrays (core.py:489, decoder.py:360-375)
+        lazy = (lambda t: t) if return_device else hostio.LazyHostArray
         decoding_res = {'log_posterior_all': conv(torch.log(res.gamma)),
                         'log_marginal_final': float(res.log_marginal.item()),
                         'posterior_all': conv(res.gamma),
                         'posterior_latent_marg': _rewrap_tsd(conv(res.gamma_lat), t_l),
                         'posterior_dynamics_marg': _rewrap_tsd(conv(res.dyn_marg), t_l),
-                        'log_one_step_predictive_marginals_all': conv(res.lmr),
+                        'log_one_step_predictive_marginals_all': lazy(res.lmr),
                         'log_likelihood_all': conv(res.ll)}
-        if T > 1:
-            G = ops.atb(res.alpha.view(T, 2 * K)[:T - 1], res.r.view(T, 2 * K)[1:])
-            log_acc = ops.xi_finalize(G, self._dev(logP), logM)
+        if T > 1 or es.shard.active:
+            log_acc = self._transition_counts(es, res, logP, logM)
             tp = compute_transition_posterior_prob(log_acc)
-            decoding_res.update({k: conv(v) for k, v in tp.items()})
+            decoding_res.update({k: lazy(v) for k, v in tp.items()})
         self._last_estep_info = {"n_chain": res.plan.n_chain, "relay_fwd": res.n_relay_fwd,
                                  "relay_bwd": res.n_relay_bwd, "seam_err_fwd": res.seam_err_fwd,
                                  "seam_err_bwd": res.seam_err_bwd}
@@ -339,9 +370,13 @@ class PoissonGPLVMJump1D:
                save_every=None,
                m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6,
                posterior_init_kwargs={'random_scale': 0.1}, verboase=True, return_device=False,
+               time_sharded=False, group=None,
                **kwargs):
         """reference core.py:829-849 -> :592-713.  Per iteration: M-step (statistics + Adam) on the
-        current posterior, tuning, E-step; ``em_res`` has the reference's keys."""
+        current posterior, tuning, E-step; ``em_res`` has the reference's keys.
+        time_sharded=True (one process per GPU under torch.distributed): ``y`` and ``log_posterior_init`` are
+        this rank's contiguous block of time bins; T-sized results cover that block, while ``params``,
+        ``tuning`` and the log marginals are global and identical on every rank."""
         y_in, t_l = _unwrap_tsd(y)
         hyperparam_ = dict(hyperparam)
         prior_std = hyperparam_.get('param_prior_std', self.param_prior_std)
@@ -367,7 +402,7 @@ class PoissonGPLVMJump1D:
         if log_posterior_init is None:
             log_posterior_init, _ = self.init_latent_posterior(T, key, **posterior_init_kwargs)
         loop = EMLoop(self, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
-                      m_step_step_size, m_step_maxiter, m_step_tol)
+                      m_step_step_size, m_step_maxiter, m_step_tol, shard=TimeShard(group) if time_sharded else None)
         self.opt_state_init_fun = ops.AdamState
         W, state, es = loop.W, loop.state, loop.es
 
@@ -376,6 +411,8 @@ class PoissonGPLVMJump1D:
                  'log_marginal_saved': []}
         estep_info = []
         conv = (lambda t: t) if return_device else self._host
+        # jax device arrays in the reference (core.py:672-675, :703): copied to the host on first use
+        lazy_log = (lambda t: torch.log(t)) if return_device else (lambda t: hostio.LazyHostArray(t, torch.log))
         res = None
         for i in range(n_iter):
             last = i == n_iter - 1
@@ -386,7 +423,7 @@ class PoissonGPLVMJump1D:
             lml_dev.append(res.log_marginal)
             estep_info.append((res.n_relay_fwd, res.n_relay_bwd, res.seam_err_fwd, res.seam_err_bwd))
             if snap:
-                saved['log_posterior_all_saved'].append(conv(torch.log(res.gamma)))
+                saved['log_posterior_all_saved'].append(lazy_log(res.gamma))
                 saved['params_saved'].append(conv(W.clone()))
                 saved['tuning_saved'].append(conv(tuning))
                 saved['log_marginal_saved'].append(res.log_marginal)
@@ -418,7 +455,7 @@ class PoissonGPLVMJump1D:
                        'log_marginal_l': [v for v in lml_host],
                        'm_step_res_l': m_step_res_l})
         if n_iter > 0:
-            em_res.update({'log_posterior_final': conv(torch.log(res.gamma)),
+            em_res.update({'log_posterior_final': lazy_log(res.gamma),
                            'log_marginal': lml_host[-1],
                            'posterior': conv(res.gamma),
                            'posterior_latent_marg': _rewrap_tsd(conv(res.gamma_lat), t_l),

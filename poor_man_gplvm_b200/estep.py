@@ -2,11 +2,14 @@
 
 Host-side orchestration of reference ``decoder.smooth_all_step_combined_ma_chunk``
 (poor_man_gplvm/decoder.py:258-332).  The reference walks 10 000-bin chunks
-sequentially; here the time axis is cut into ``n_chain`` chunks that run
-concurrently.  A chain warms up over ``halo`` bins from the uniform message;
-``pmg_seam_check`` then compares its warmed-up message with the neighbouring
-chain's true one, and any seam above tolerance is repaired by relaying the
-exact carry (worst case this degenerates to the reference's sequential walk,
+sequentially; here the time axis is cut into ``n_chain`` chunks ("chains") that run
+concurrently, on one GPU or on a contiguous time block per rank.  A chain warms
+up over ``halo`` bins starting from the previous pass's message at that bin (or
+the stationary distribution of the prior chain on the first pass);
+``pmg_seam_check`` then compares the warmed-up message with the neighbouring
+chain's true one, and failing chains are restarted in parallel sweeps from a
+snapshot of the neighbour's boundary message until every seam agrees to
+``seam_tol`` (worst case this degenerates to the reference's sequential walk,
 so the result never depends on the chunking beyond ``seam_tol``).
 """
 from __future__ import annotations
@@ -16,6 +19,7 @@ import os
 import torch
 
 from . import ops
+from .shard import TimeShard
 
 DEFAULT_HALO = int(os.environ.get("PMG_HALO", "256"))
 DEFAULT_SEAM_TOL = float(os.environ.get("PMG_SEAM_TOL", "1e-5"))
@@ -33,18 +37,17 @@ def plan_chunks(n_core, halo, sm_count, chains_per_sm=8):
 
 
 class EStepResult:
+    """Tensors cover this rank's core bins only (views into the E-step buffers)."""
     __slots__ = ("ll", "alpha", "lmr", "gamma", "gamma_lat", "dyn_marg", "r", "tw", "log_marginal",
-                 "n_relay_fwd", "n_relay_bwd", "seam_err_fwd", "seam_err_bwd", "plan")
+                 "n_relay_fwd", "n_relay_bwd", "seam_err_fwd", "seam_err_bwd", "plan", "alpha_ext", "r_ext", "core")
 
 
 class EStep:
-    """Buffers and launch plan for repeated E-steps over the same spike matrix."""
+    """Buffers and launch plan for repeated E-steps over the same spike matrix (this rank's block)."""
 
     def __init__(self, y, op, ma_neuron=None, ma_latent=None, likelihood_scale=1.0, halo=None, seam_tol=None,
-                 chunk_len=None, emission_impl=0):
-        self.y = y
+                 chunk_len=None, emission_impl=0, shard=None):
         self.op = op
-        self.T, self.N = y.shape
         self.K = op.K
         self.dev = y.device
         self.ma_neuron = ma_neuron
@@ -53,21 +56,32 @@ class EStep:
         self.halo = DEFAULT_HALO if halo is None else int(halo)
         self.seam_tol = DEFAULT_SEAM_TOL if seam_tol is None else float(seam_tol)
         self.emission_impl = emission_impl
+        self.shard = shard if shard is not None else TimeShard(None, single=True)
+        self.T_core, self.N = y.shape
+        # neighbours' bins for the warm-ups that cross the block boundary (fetched once; y is constant)
+        y_ext, self.h_left, self.h_right = self.shard.halo_exchange(y, self.halo)
+        self.y = y_ext
+        self.T = y_ext.shape[0]
+        self.core = slice(self.h_left, self.h_left + self.T_core)
         self.sm_count = torch.cuda.get_device_properties(self.dev).multi_processor_count
         if chunk_len is None:
-            chunk_len = plan_chunks(self.T, self.halo, self.sm_count)
-        self.chunk_len = int(min(max(1, chunk_len), self.T))
-        self.plan = ops.make_plan(self.T, 0, self.T, self.chunk_len, self.halo, True, True, self.scale)
+            chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count)
+        self.chunk_len = int(min(max(1, chunk_len), self.T_core))
+        self.plan = ops.make_plan(self.T, self.core.start, self.core.stop, self.chunk_len, self.halo,
+                                  self.shard.is_first, self.shard.is_last, self.scale)
         S = self.plan.n_chain
+        self.S = S
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.lgam = ops.lgamma_rowsum(y, ma_neuron)
-        self.y16 = ops.CountsF16(y) if emission_impl == 0 else None
+        self.lgam = ops.lgamma_rowsum(self.y, ma_neuron)
+        self.y16 = ops.CountsF16(self.y) if emission_impl == 0 else None
         self.ll = torch.empty((self.T, self.K), **f32)
-        self.alpha = torch.empty((self.T, 2, self.K), **f32)
-        self.lmr = torch.empty(self.T, **f32)
+        self.alpha = torch.zeros((self.T, 2, self.K), **f32)
+        self.lmr = torch.zeros(self.T, **f32)
         self.halo_state = torch.zeros((S, 2, self.K), **f32)
         self.beta_halo = torch.zeros((S, 2, self.K), **f32)
-        self.beta_end = torch.zeros((S, 2, self.K), **f32)
+        self.beta_end = torch.zeros((S + 1, 2, self.K), **f32)     # [S] = the right neighbour's first chain
+        self.truth = torch.zeros((S, 2, self.K), **f32)
+        self.truth_left = None
         self.tw_partial = torch.zeros((S, self.K), **f32)
         # warm-up starts: ping-pong buffers holding, for every chain, the message of the previous pass
         # at the bin where its warm-up starts (forward and backward); before the first pass the forward
@@ -76,8 +90,13 @@ class EStep:
         self.bwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
         self.warm_cur = 0
         self.warm_valid = False
-        self.err = torch.zeros(2 * max(S, 1), **f32)
-        self.err_host = torch.zeros(2 * max(S, 1), dtype=torch.float32).pin_memory()
+        self.err = torch.zeros(2 * S, **f32)
+        self.err_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
+        # rows of alpha holding the true message in front of chain c (c >= 1): bin t_begin(c) - 1
+        self.rows_f = self.core.start + torch.arange(1, S, device=self.dev) * self.chunk_len - 1
+        # which seams exist: forward seam c sits in front of chain c; backward seam c behind chain c
+        self.f_lo = 0 if not self.shard.is_first else 1
+        self.b_hi = S if not self.shard.is_last else S - 1
 
     # -- pieces ---------------------------------------------------------------------------
     def emission(self, tuning):
@@ -85,20 +104,44 @@ class EStep:
                      impl=self.emission_impl)
         return self.ll
 
-    def _check_fwd(self, n, first_chain=1):
-        # est = halo_state[s], truth = alpha[t_begin(s)-1], s = first_chain..first_chain+n-1
-        K2 = 2 * self.K
-        est = self.halo_state.data_ptr() + first_chain * K2 * 4
-        truth = self.alpha.data_ptr() + (first_chain * self.chunk_len - 1) * K2 * 4
-        ops.seam_check(n, K2, est, K2, truth, self.chunk_len * K2, self.err[first_chain:first_chain + n])
+    def _exchange_fwd(self):
+        """After a forward pass: the last true alpha goes right (seam truth of the neighbour's first
+        chain), the first true alpha goes left (normaliser of the neighbour's last backward seam)."""
+        if not self.shard.active:
+            return
+        first = self.alpha[self.core.start].reshape(-1)
+        last = self.alpha[self.core.stop - 1].reshape(-1)
+        from_left, from_right = self.shard.boundary(first, last)
+        if from_left is not None:
+            self.truth_left = from_left.view(2, self.K)
+        if from_right is not None:
+            self.alpha[self.core.stop].copy_(from_right.view(2, self.K))
 
-    def _check_bwd(self, n, first_chain=0):
-        # est = beta_halo[s], truth = beta_end[s+1], s = first_chain..first_chain+n-1
-        K2 = 2 * self.K
-        S = self.plan.n_chain
-        est = self.beta_halo.data_ptr() + first_chain * K2 * 4
-        truth = self.beta_end.data_ptr() + (first_chain + 1) * K2 * 4
-        ops.seam_check(n, K2, est, K2, truth, K2, self.err[S + first_chain:S + first_chain + n])
+    def _exchange_bwd(self):
+        """After a backward pass: beta at the first core bin goes left (seam truth of the neighbour's last chain)."""
+        if not self.shard.active:
+            return
+        _, from_right = self.shard.boundary(self.beta_end[0].reshape(-1), None)
+        if from_right is not None:
+            self.beta_end[self.S].copy_(from_right.view(2, self.K))
+
+    def _check_fwd(self):
+        S, K2 = self.S, 2 * self.K
+        if S > 1:
+            self.truth[1:] = self.alpha[self.rows_f]
+        if self.f_lo == 0:
+            self.truth[0] = self.truth_left
+        n = S - self.f_lo
+        if n > 0:
+            ops.seam_check(n, K2, self.halo_state[self.f_lo:].data_ptr(), K2, self.truth[self.f_lo:].data_ptr(), K2,
+                           self.err[self.f_lo:S])
+
+    def _check_bwd(self):
+        S, K2 = self.S, 2 * self.K
+        n = self.b_hi
+        if n > 0:
+            ops.seam_check(n, K2, self.beta_halo.data_ptr(), K2, self.beta_end[1:].data_ptr(), K2,
+                           self.err[S:S + n])
 
     def _read_err(self):
         self.err_host.copy_(self.err, non_blocking=True)
@@ -106,10 +149,9 @@ class EStep:
         return self.err_host
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None):
-        """One E-step.  Returns an EStepResult whose tensors alias this object's buffers.
-        gamma16: optional [2,T,ldg] fp16 buffer that receives the hi/lo pieces of the latent posterior."""
-        S = self.plan.n_chain
-        K = self.K
+        """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
+        the hi/lo pieces of the latent posterior."""
+        S, K = self.S, self.K
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.emission(tuning)
         ops.phase("emission")
@@ -122,68 +164,81 @@ class EStep:
         f_in = self.fwarm[cur] if self.warm_valid else getattr(self.op, "stationary", None)
         b_in = self.bwarm[cur] if self.warm_valid else None
 
-        def bwd(mode=0, ids=None, carry=None):
+        def fwd(mode=0, ids=None):
+            ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr,
+                        halo_state=(self.halo_state if mode == 0 else None), mode=mode, chain_ids=ids,
+                        warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt])
+
+        def bwd(mode=0, ids=None):
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
-                         mode=mode, chain_ids=ids, gamma16=gamma16, warm_in=(b_in if mode == 0 else carry),
-                         warm_out=self.bwarm[nxt])
+                         mode=mode, chain_ids=ids, gamma16=gamma16,
+                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=self.bwarm[nxt])
 
-        ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=self.halo_state, warm_in=f_in,
-                    warm_out=self.fwarm[nxt])
-        n_relay_f = n_relay_b = 0
-        if S > 1:
-            self._check_fwd(S - 1)
+        fwd()
+        self._exchange_fwd()
+        self._check_fwd()
         ops.phase("forward")
         bwd()
+        self._exchange_bwd()
+        self._check_bwd()
         ops.phase("backward")
-        if S > 1:
-            self._check_bwd(S - 1)
+
+        n_relay_f = n_relay_b = 0
+        ef = eb = torch.zeros(0)
+        if S > 1 or self.shard.active:
             err = self._read_err()
-            ef = err[1:S].clone()            # ef[c-1]: seam in front of chain c
-            eb = err[S:2 * S - 1].clone()    # eb[c]:   seam behind chain c
+            ef = err[self.f_lo:S].clone()         # ef[i]: seam in front of chain f_lo + i
+            eb = err[S:S + self.b_hi].clone()     # eb[c]: seam behind chain c
             # Seam repair = parallel (Jacobi) sweeps: every chain whose incoming message was off restarts,
-            # all at once, from a snapshot of its neighbour's current boundary message; the seams are then
-            # re-verified against the messages those restarts produced.  Each sweep extends the effective
-            # warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length (in the worst,
-            # non-mixing case it degenerates to the reference's sequential walk).
-            rows = torch.arange(1, S, device=self.dev) * self.chunk_len - 1      # bin t_begin(c)-1, c = 1..S-1
+            # all at once (on all ranks), from a snapshot of its neighbour's current boundary message; the
+            # seams are then re-verified against the messages those restarts produced.  Each sweep extends
+            # the effective warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length.
             redo_bwd = False
-            for _ in range(S):
-                bad = torch.nonzero(ef > self.seam_tol).flatten() + 1
-                if not bad.numel():
+            for _ in range(S * self.shard.world + 1):
+                bad = torch.nonzero(ef > self.seam_tol).flatten() + self.f_lo
+                if self.shard.max_int(bad.numel(), self.dev) == 0:
                     break
                 redo_bwd = True
                 n_relay_f += int(bad.numel())
-                ids = bad.to(device=self.dev, dtype=torch.int32)
-                self.halo_state[ids.long()] = self.alpha[rows[ids.long() - 1]]   # carry snapshot = new "estimate"
-                ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, halo_state=None, mode=1,
-                            chain_ids=ids, warm_in=self.halo_state, warm_out=self.fwarm[nxt])
-                self._check_fwd(S - 1)
-                ef = self._read_err()[1:S].clone()
+                if bad.numel():
+                    ids = bad.to(device=self.dev, dtype=torch.int32)
+                    self.halo_state[ids.long()] = self.truth[ids.long()]      # carry snapshot = new "estimate"
+                    fwd(mode=1, ids=ids)
+                self._exchange_fwd()
+                self._check_fwd()
+                ef = self._read_err()[self.f_lo:S].clone()
             if redo_bwd:
                 bwd()
-                self._check_bwd(S - 1)
-                eb = self._read_err()[S:2 * S - 1].clone()
-            for _ in range(S):
+                self._exchange_bwd()
+                self._check_bwd()
+                eb = self._read_err()[S:S + self.b_hi].clone()
+            for _ in range(S * self.shard.world + 1):
                 bad = torch.nonzero(eb > self.seam_tol).flatten()
-                if not bad.numel():
+                if self.shard.max_int(bad.numel(), self.dev) == 0:
                     break
                 n_relay_b += int(bad.numel())
-                ids = bad.to(device=self.dev, dtype=torch.int32)
-                self.beta_halo[ids.long()] = self.beta_end[ids.long() + 1]
-                bwd(mode=1, ids=ids, carry=self.beta_halo)
-                self._check_bwd(S - 1)
-                eb = self._read_err()[S:2 * S - 1].clone()
-        else:
-            ef = eb = torch.zeros(0)
-
-        if S > 1:
+                if bad.numel():
+                    ids = bad.to(device=self.dev, dtype=torch.int32)
+                    self.beta_halo[ids.long()] = self.beta_end[ids.long() + 1]
+                    bwd(mode=1, ids=ids)
+                self._exchange_bwd()
+                self._check_bwd()
+                eb = self._read_err()[S:S + self.b_hi].clone()
             self.warm_cur, self.warm_valid = nxt, True
+
+        c = self.core
         res = EStepResult()
-        res.ll, res.alpha, res.lmr = self.ll, self.alpha, self.lmr
-        res.gamma, res.gamma_lat, res.dyn_marg, res.r = gamma, gamma_lat, dyn, r
+        res.core = c
+        res.ll, res.alpha, res.lmr = self.ll[c], self.alpha[c], self.lmr[c]
+        res.alpha_ext, res.r_ext = self.alpha, r
+        res.gamma = gamma[c] if gamma is not None else None
+        res.gamma_lat = gamma_lat[c] if gamma_lat is not None else None
+        res.dyn_marg = dyn[c] if dyn is not None else None
+        res.r = r[c] if r is not None else None
+        # local sums; the caller all-reduces them together with the spike-weighted statistics
         res.tw = self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
-        res.log_marginal = self.lmr.sum(dtype=torch.float64)
+        res.log_marginal = self.lmr[c].sum(dtype=torch.float64)
         res.n_relay_fwd, res.n_relay_bwd = n_relay_f, n_relay_b
         res.seam_err_fwd = float(ef.max()) if ef.numel() else 0.0
         res.seam_err_bwd = float(eb.max()) if eb.numel() else 0.0

@@ -1,0 +1,99 @@
+"""Time sharding over ranks (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+Rank r owns a contiguous block of time bins.  The only exchanges of the EM hot path are
+  * once per fit: ``halo`` rows of the spike matrix from each neighbour (warm-up bins of the scan),
+  * per pass: one boundary message (2K floats) to each neighbour,
+  * per EM iteration: one all-reduce of the packed sufficient statistics (K*N + K + 1 floats),
+  * per seam-repair sweep: one scalar all-reduce (does any rank still have a failing seam?).
+The reference has no multi-device code; this layer is new.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class TimeShard:
+    def __init__(self, group=None, single=False):
+        self.group = group
+        self.active = (not single) and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.world = dist.get_world_size(group) if self.active else 1
+
+    @property
+    def is_first(self):
+        return self.rank == 0
+
+    @property
+    def is_last(self):
+        return self.rank == self.world - 1
+
+    def _peer(self, r):
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def _exchange(self, to_left, to_right, like_left, like_right):
+        """Send `to_left` to rank-1 and `to_right` to rank+1; receive into fresh tensors shaped like
+        `like_left` (from rank-1) and `like_right` (from rank+1).  Any of them may be None."""
+        ops, from_left, from_right = [], None, None
+        if not self.is_first:
+            if to_left is not None:
+                ops.append(dist.P2POp(dist.isend, to_left.contiguous(), self._peer(self.rank - 1), self.group))
+            if like_left is not None:
+                from_left = torch.empty_like(like_left)
+                ops.append(dist.P2POp(dist.irecv, from_left, self._peer(self.rank - 1), self.group))
+        if not self.is_last:
+            if to_right is not None:
+                ops.append(dist.P2POp(dist.isend, to_right.contiguous(), self._peer(self.rank + 1), self.group))
+            if like_right is not None:
+                from_right = torch.empty_like(like_right)
+                ops.append(dist.P2POp(dist.irecv, from_right, self._peer(self.rank + 1), self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return from_left, from_right
+
+    def halo_exchange(self, x, halo):
+        """x: [T_core, ...] block of this rank.  Returns (x_ext, h_left, h_right) where x_ext has the
+        last `halo` rows of the left neighbour in front and the first `halo` rows of the right one behind."""
+        if not self.active or halo <= 0:
+            return x, 0, 0
+        if x.shape[0] < halo:
+            raise ValueError("time block of %d bins is shorter than the halo %d" % (x.shape[0], halo))
+        head, tail = x[:halo], x[-halo:]
+        from_left, from_right = self._exchange(head, tail, tail, head)
+        parts, hl, hr = [], 0, 0
+        if from_left is not None:
+            parts.append(from_left); hl = halo
+        parts.append(x)
+        if from_right is not None:
+            parts.append(from_right); hr = halo
+        return torch.cat(parts, dim=0).contiguous(), hl, hr
+
+    def boundary(self, to_left, to_right):
+        """One message to each neighbour (same shape everywhere); returns (from_left, from_right)."""
+        if not self.active:
+            return None, None
+        # every rank calls with the same pattern: something arrives from the left only if ranks send
+        # rightwards (to_right given), and from the right only if ranks send leftwards
+        like = to_left if to_left is not None else to_right
+        return self._exchange(to_left, to_right, like if to_right is not None else None,
+                              like if to_left is not None else None)
+
+    def allreduce_sum_(self, *tensors):
+        """In-place sum over ranks of several tensors packed into one collective."""
+        if not self.active:
+            return
+        flat = torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        o = 0
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[o:o + n].reshape(t.shape).to(t.dtype))
+            o += n
+
+    def max_int(self, v, device):
+        if not self.active:
+            return int(v)
+        t = torch.tensor([int(v)], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())

@@ -104,3 +104,17 @@ def test_product_sources_never_touch_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_lazy_host_array_behaves_like_numpy():
+    import torch
+    from poor_man_gplvm_b200.hostio import LazyHostArray, to_numpy
+    t = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4) / 10
+    a = LazyHostArray(t, torch.exp)
+    want = np.exp(np.arange(24, dtype=np.float32).reshape(2, 3, 4) / 10)
+    assert a.shape == (2, 3, 4) and a.ndim == 3 and len(a) == 2 and a.dtype == np.float32
+    assert np.allclose(np.asarray(a), want)
+    assert np.allclose(a[1, :, 2], want[1, :, 2])
+    assert np.allclose(a - want, 0, atol=1e-5) and np.allclose(want - a, 0, atol=1e-5) and np.allclose(np.log(a), np.log(want))
+    assert np.isclose(a.sum(), want.sum(), rtol=1e-5) and a.argmax() == want.argmax()
+    assert np.array_equal(to_numpy(t), t.numpy())
