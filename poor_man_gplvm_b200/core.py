@@ -10,6 +10,9 @@ tensors and skip the device->host copies).
 """
 from __future__ import annotations
 
+import os
+import time
+
 import numpy as np
 import torch
 
@@ -35,6 +38,26 @@ def _rewrap_tsd(arr, t_l):
         return nap.TsdFrame(d=arr, t=t_l)
     except Exception:
         return arr
+
+
+class _Timing:
+    """Optional wall-clock breakdown of fit_em (PMG_TIMING=1): synchronises at every mark."""
+
+    def __init__(self):
+        self.on = bool(os.environ.get("PMG_TIMING"))
+        self.t = time.perf_counter()
+        self.marks = []
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.marks.append((name, now - self.t))
+            self.t = now
+
+    def report(self):
+        if self.on:
+            print("fit_em timing: " + ", ".join("%s %.3fs" % m for m in self.marks), flush=True)
 
 
 def _seed_from_key(key):
@@ -388,7 +411,9 @@ class PoissonGPLVMJump1D:
         self.p_move_to_jump = hyperparam_.get('p_move_to_jump', self.p_move_to_jump)
         self.p_jump_to_move = hyperparam_.get('p_jump_to_move', self.p_jump_to_move)
 
+        tm = _Timing()
         y_dev = self._dev(y_in)                       # the one host->device copy of the spikes
+        tm.mark("h2d_y")
         T, K = y_dev.shape[0], self.n_latent_bin
         if save_every is None:
             save_every = n_iter
@@ -405,6 +430,7 @@ class PoissonGPLVMJump1D:
                       m_step_step_size, m_step_maxiter, m_step_tol, shard=TimeShard(group) if time_sharded else None)
         self.opt_state_init_fun = ops.AdamState
         W, state, es = loop.W, loop.state, loop.es
+        tm.mark("setup")
 
         lml_dev, m_hist = [], []
         saved = {'log_posterior_all_saved': [], 'params_saved': [], 'tuning_saved': [], 'iter_saved': [],
@@ -429,6 +455,7 @@ class PoissonGPLVMJump1D:
                 saved['log_marginal_saved'].append(res.log_marginal)
                 saved['iter_saved'].append(i)
 
+        tm.mark("em_loop")
         lml_host = torch.stack(lml_dev).cpu().numpy().astype(np.float32) if lml_dev else np.zeros(0, np.float32)
         saved['log_marginal_saved'] = [np.float32(v.item()) for v in saved['log_marginal_saved']]
         n_its = torch.cat([h[2] for h in m_hist]).cpu().numpy() if m_hist else np.zeros(0, np.int32)
@@ -460,6 +487,8 @@ class PoissonGPLVMJump1D:
                            'posterior': conv(res.gamma),
                            'posterior_latent_marg': _rewrap_tsd(conv(res.gamma_lat), t_l),
                            'posterior_dynamics_marg': _rewrap_tsd(conv(res.dyn_marg), t_l)})
+        tm.mark("outputs")
+        tm.report()
         return em_res
 
     def predict_expected_rate(self, post_latent_marg, tuning=None):

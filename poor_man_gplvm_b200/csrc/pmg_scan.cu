@@ -288,10 +288,18 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
       s2[1] += al1[q];
     }
     group_sum<WPC, 2>(s2, red, red_par, wig, lane, bar_id);
-    const float inv = 1.f / (s2[0] + s2[1]);
+    const float tot = s2[0] + s2[1];
+    if (tot > 0.f && tot < 3.0e38f) {
+      const float inv = 1.f / tot;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) { al0[q] *= inv; al1[q] *= inv; }
-    p1 = (M01 * s2[0] + M11 * s2[1]) * inv * invK;
+      for (int q = 0; q < Q; ++q) { al0[q] *= inv; al1[q] *= inv; }
+      p1 = (M01 * s2[0] + M11 * s2[1]) * inv * invK;
+    } else {   // unusable initial message: uniform
+      const float u = 0.5f * invK;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { al0[q] = valid[q] ? u : 0.f; al1[q] = al0[q]; }
+      p1 = (M01 * 0.5f + M11 * 0.5f) * invK;
+    }
   } else {
     const float u = 0.5f * invK;
 #pragma unroll
@@ -690,6 +698,21 @@ static bool bulk_ok(const BwdParams& p) {
   return (((uintptr_t)p.c.ll | (uintptr_t)p.alpha | (uintptr_t)p.gamma16) & 15) == 0;
 }
 
+template <bool FWD, int Q, int WT, int NW, int OB, typename P>
+static int bulk_launch(const P& p, int n_groups, cudaStream_t st) {
+  if constexpr (FWD) return launch_fwd_bulk<Q, WT, NW, OB>(p, n_groups, st);
+  else return launch_bwd_bulk<Q, WT, NW, OB>(p, n_groups, st);
+}
+template <bool FWD, int Q, int WT, typename P>
+static int bulk_variant(const P& p, int n_groups, cudaStream_t st, int var) {
+  switch (var) {
+    case 122: return bulk_launch<FWD, Q, WT, 12, 2>(p, n_groups, st);
+    case 162: return bulk_launch<FWD, Q, WT, 16, 2>(p, n_groups, st);
+    case 161: return bulk_launch<FWD, Q, WT, 16, 1>(p, n_groups, st);
+    default: return bulk_launch<FWD, Q, WT, 8, 2>(p, n_groups, st);
+  }
+}
+
 // choose (Q, WPC): smallest group that covers K with at most 16 bins per thread
 template <bool FWD, typename P>
 static int dispatch(const P& p, int n_groups, cudaStream_t st) {
@@ -697,27 +720,18 @@ static int dispatch(const P& p, int n_groups, cudaStream_t st) {
   const bool reg = p.c.tr.kind == 0 && p.c.tr.W <= kRegWT;
   // whole-row bulk copies need 16-byte rows: K % 8 == 0 (fp16 posterior pieces), ld % 4 == 0
   static const bool direct_only = std::getenv("PMG_SCAN_DIRECT") != nullptr;
-  // warps (= chains) per CTA of the bulk kernels: 16 (one staging buffer, <= 128 registers) or 8 (two buffers)
-  static const int nw_fwd = std::getenv("PMG_SCAN_NW_FWD") ? std::atoi(std::getenv("PMG_SCAN_NW_FWD")) : 16;
-  static const int nw_bwd = std::getenv("PMG_SCAN_NW_BWD") ? std::atoi(std::getenv("PMG_SCAN_NW_BWD")) : 8;
-  const bool nw16 = (FWD ? nw_fwd : nw_bwd) == 16;
+  // bulk-kernel variant = warps (chains) per CTA * 10 + output staging buffers; tunable for experiments
+  static const int var_fwd = std::getenv("PMG_SCAN_VAR_FWD") ? std::atoi(std::getenv("PMG_SCAN_VAR_FWD")) : 82;
+  static const int var_bwd = std::getenv("PMG_SCAN_VAR_BWD") ? std::atoi(std::getenv("PMG_SCAN_VAR_BWD")) : 82;
+  const int var = FWD ? var_fwd : var_bwd;
   const bool w5 = p.c.tr.W <= 5;
   const bool bulk = reg && !direct_only && (K % 8 == 0) && (p.c.ldll % 4 == 0) && bulk_ok(p) && p.c.scale > 0.f;
 #define PMG_CASE(Qv, WPCv)                                                                     \
   do {                                                                                         \
     if (bulk && WPCv == 1) {                                                                   \
       int rc_;                                                                                 \
-      if constexpr (FWD) {                                                                     \
-        if (w5) rc_ = nw16 ? launch_fwd_bulk<Qv, 5, 16, 1>(p, n_groups, st)                    \
-                           : launch_fwd_bulk<Qv, 5, 8, 2>(p, n_groups, st);                    \
-        else rc_ = nw16 ? launch_fwd_bulk<Qv, 10, 16, 1>(p, n_groups, st)                      \
-                        : launch_fwd_bulk<Qv, 10, 8, 2>(p, n_groups, st);                      \
-      } else {                                                                                 \
-        if (w5) rc_ = nw16 ? launch_bwd_bulk<Qv, 5, 16, 1>(p, n_groups, st)                    \
-                           : launch_bwd_bulk<Qv, 5, 8, 2>(p, n_groups, st);                    \
-        else rc_ = nw16 ? launch_bwd_bulk<Qv, 10, 16, 1>(p, n_groups, st)                      \
-                        : launch_bwd_bulk<Qv, 10, 8, 2>(p, n_groups, st);                      \
-      }                                                                                        \
+      if (w5) rc_ = bulk_variant<FWD, Qv, 5>(p, n_groups, st, var);                           \
+      else rc_ = bulk_variant<FWD, Qv, 10>(p, n_groups, st, var);                              \
       if (rc_ != PMG_ERR_UNSUPPORTED_SHAPE) return rc_;                                        \
     }                                                                                          \
     if (reg) {                                                                                 \

@@ -142,6 +142,12 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
     S1 += v1[q];
   }
   S0 = warp_sum(S0); S1 = warp_sum(S1);
+  if (!(S0 + S1 > 0.f) || !(S0 + S1 < 3.0e38f)) {
+    // unusable initial message (all zero / non-finite): fall back to the uniform one
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { v0[q] = (x0 + q < K) ? 0.5f * invK : 0.f; v1[q] = v0[q]; }
+    S0 = 0.5f; S1 = 0.5f;
+  }
   float inv_prev = 1.f / (S0 + S1);
 
   // ---- fill the input ring
@@ -350,6 +356,17 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
         b0[q] = ok ? (init ? init[x0 + q] : 1.f) : 0.f;
         b1[q] = ok ? (init ? init[K + x0 + q] : 1.f) : 0.f;
         r0[q] = 0.f; r1[q] = 0.f;
+      }
+      {
+        // unusable initial message (all zero / non-finite): fall back to the all-ones one
+        float sb = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) sb += b0[q] + b1[q];
+        sb = warp_sum(sb);
+        if (!(sb > 0.f) || !(sb < 3.0e38f)) {
+#pragma unroll
+          for (int q = 0; q < Q; ++q) { b0[q] = (x0 + q < K) ? 1.f : 0.f; b1[q] = b0[q]; }
+        }
       }
       __syncwarp();
     } else {

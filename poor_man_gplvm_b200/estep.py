@@ -88,6 +88,14 @@ class EStep:
         # warm-up starts from the stationary distribution of the prior chain (exact for flat likelihoods)
         self.fwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
         self.bwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
+        # entries no local chain ever writes (the warm-up of the first chain starts in the left
+        # neighbour's bins, the last chain's backward warm-up in the right neighbour's): keep them at the
+        # first-pass defaults — stationary prior for the forward message, all-ones for the backward one
+        stat = getattr(op, "stationary", None)
+        for buf in self.fwarm:
+            buf[0] = stat if stat is not None else 0.5 / self.K
+        for buf in self.bwarm:
+            buf[S - 1] = 1.0
         self.warm_cur = 0
         self.warm_valid = False
         self.err = torch.zeros(2 * S, **f32)
