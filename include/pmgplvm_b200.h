@@ -48,6 +48,18 @@ int pmg_emission_prepare(int K, int N, const float* tuning, const float* ma_neur
 int pmg_emission_lgamma_rowsum(int64_t T, int N, const float* y, int64_t ldy,
                                const float* ma_neuron, float* lgam, pmg_stream_t stream);
 
+/* Row terms with the full mask surface: ma_neuron is NULL, a vector [N] (ld_mask = 0) or a spatio-temporal
+ * mask [T, ld_mask] (decoder.py:291-294).  lgam[t] = sum_n m lgamma(y+1); ysum[t] (optional) = sum_n m y. */
+int pmg_emission_row_terms(int64_t T, int N, const float* y, int64_t ldy, const float* ma_neuron,
+                           int64_t ld_mask, float* lgam, float* ysum, pmg_stream_t stream);
+
+/* Augmented right-hand operand [rows_out, ldo] (rows >= K zero) for the options the plain GEMM form lacks:
+ *  mode 1  [T,N] neuron mask: B[k,:] = [log lam_k | -lam_k], paired with A = [m*y | m]; lam_sum = 0;
+ *  mode 2  per-bin dt (decoder.py:73-85): B[k,:] = [ma log(tun_k + 1e-20) | -sum_n ma tun_kn], paired with
+ *          A = [y | dt_t]; lam_sum[k] = 1e-20 sum_n ma; the caller adds -log(dt_t) * ysum[t] to lgam[t]. */
+int pmg_emission_prepare_aug(int K, int N, const float* tuning, const float* ma_neuron, float dt, int mode,
+                             int rows_out, float* out, int64_t ldo, float* lam_sum, pmg_stream_t stream);
+
 /* fp32 operands on CUDA-core tiles: for counts that are not exact in fp16 (non-integer y,
  * decoder.py:37-38) and as the cross-check of the tensor-core kernel below. */
 int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, const float* loglam,

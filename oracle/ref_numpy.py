@@ -1,6 +1,7 @@
 """NumPy restatement of the reference's EM hot path (TEST INFRASTRUCTURE ONLY).
 
-PARITY UNPINNED — see ``oracle/__init__.py``.  Every function names the reference
+Pinned against the reference's own source files run on ``oracle/jaxshim`` (golden vectors in
+``tests/golden``; what that does and does not cover: ``oracle/__init__.py``).  Every function names the reference
 lines it restates (paths relative to ``/root/reference/poor_man_gplvm/``).  The
 arithmetic follows the reference's *operation order* (log space, one
 ``logsumexp`` per reduction, per-step ``[2,2,K,K]`` joint in the smoother) so

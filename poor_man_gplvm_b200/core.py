@@ -262,11 +262,12 @@ class PoissonGPLVMJump1D:
             ma_neuron = self.ma_neuron_default
         if ma_latent is None:
             ma_latent = self.ma_latent_default
-        ma_n = np.asarray(self._host(ma_neuron), dtype=np.float32)
-        if ma_n.ndim == 2:
-            raise NotImplementedError("spatio-temporal ma_neuron [T,N] is not on the CUDA path yet (SURVEY F4)")
-        ma_l = np.asarray(self._host(ma_latent), dtype=np.float32)
-        return self._dev(ma_n), self._dev(ma_l)
+        ma_n = self._dev(ma_neuron)
+        if ma_n.dim() == 2 and tuple(ma_n.shape) != (T, self.n_neuron):
+            raise ValueError("ma_neuron must be [n_neuron] or [T, n_neuron], got %s" % (tuple(ma_n.shape),))
+        if ma_n.dim() == 1 and ma_n.shape[0] != self.n_neuron:
+            raise ValueError("ma_neuron must be [n_neuron] or [T, n_neuron], got %s" % (tuple(ma_n.shape),))
+        return ma_n, self._dev(ma_latent)
 
     def _transition_counts(self, es, res, logP, logM):
         """log sum_t xi_t (reference decoder.py:215-221) = log(M * P * (alpha^T r)): one time-reduction GEMM
@@ -356,12 +357,17 @@ class PoissonGPLVMJump1D:
         y_dev = self._dev(y)
         T = y_dev.shape[0]
         ma_n, ma_l = self._masks(ma_neuron, ma_latent, T)
-        dt_arr = np.asarray(self._host(dt_l), dtype=np.float32)
-        if dt_arr.ndim > 0 and dt_arr.size > 1 and not np.all(dt_arr == dt_arr.flat[0]):
-            raise NotImplementedError("per-bin dt_l is not on the CUDA path yet (SURVEY F4)")
-        dt = float(dt_arr.flat[0]) if dt_arr.size else 1.0
-        lgam = ops.lgamma_rowsum(y_dev, ma_n)
-        ll = ops.emission(y_dev, self._dev(tuning), lgam, ma_n, ma_l, dt, y16=ops.CountsF16(y_dev))
+        # dt_l: scalar or per-bin [T] (reference decoder.py:124 broadcasts it to [T])
+        dt_dev = self._dev(dt_l).reshape(-1)
+        if dt_dev.numel() not in (1, T):
+            raise ValueError("dt_l must be a scalar or have one entry per time bin")
+        if dt_dev.numel() == T and T > 1 and bool((dt_dev != dt_dev[0]).any()):
+            em = ops.EmissionOperands(y_dev, ma_n, dt_l=dt_dev)
+            dt = 1.0
+        else:
+            em = ops.EmissionOperands(y_dev, ma_n)
+            dt = float(dt_dev[0].item()) if dt_dev.numel() else 1.0
+        ll = em.loglik(self._dev(tuning), ma_l, dt)
         log_post, lml = ops.naive_bayes_normalize(ll)
         conv = (lambda t: t) if return_device else self._host
         return {'log_posterior_latent': conv(log_post),

@@ -32,21 +32,81 @@ __global__ void emission_prepare_kernel(int K, int N, const float* __restrict__ 
 }
 
 // one warp per time bin
+// ma_neuron: NULL, a vector (ldm = 0) or a [T,N] matrix (ldm = row stride, decoder.py:291-294);
+// ysum (optional): masked row sums of the counts (needed by the per-bin dt path, decoder.py:73-85)
 __global__ void lgamma_rowsum_kernel(int64_t T, int N, const float* __restrict__ y, int64_t ldy,
-                                     const float* __restrict__ ma_neuron, float* __restrict__ out) {
+                                     const float* __restrict__ ma_neuron, int64_t ldm, float* __restrict__ out,
+                                     float* __restrict__ ysum) {
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
   const int lane = threadIdx.x & 31;
   const float* row = y + (size_t)t * ldy;
-  float acc = 0.f;
+  const float* mrow = ma_neuron ? ma_neuron + (size_t)t * ldm : nullptr;
+  float acc = 0.f, ys = 0.f;
   for (int n = lane; n < N; n += 32) {
     const float v = row[n];
     // lgamma(1) = lgamma(2) = 0: skip the (dominant) 0/1 counts
     const float lg = (v == 0.f || v == 1.f) ? 0.f : lgammaf(v + 1.f);
-    acc += (ma_neuron ? ma_neuron[n] : 1.f) * lg;
+    const float m = mrow ? mrow[n] : 1.f;
+    acc += m * lg;
+    ys += m * v;
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[t] = acc;
+  ys = warp_sum(ys);
+  if (lane == 0) {
+    out[t] = acc;
+    if (ysum) ysum[t] = ys;
+  }
+}
+
+// Augmented right-hand operands for the option surface that the plain GEMM form does not cover:
+//  mode 1, [T,N] neuron mask m (decoder.py:291-294): with A = [m*y | m] the product with
+//          B[k,:] = [log lam_k | -lam_k] gives sum_n m (y log lam - lam); lam_sum = 0.
+//  mode 2, per-bin dt (decoder.py:73-85): log(tun*dt + 1e-20) = log dt + log(tun + 1e-20/dt); with
+//          A = [y | dt_t] and B[k,:] = [ma log(tun_k + 1e-20) | -sum_n ma tun_kn] the product gives the
+//          dt-dependent part; lam_sum = 1e-20 * sum_n ma.  Exact up to the position of the 1e-20 floor
+//          (relative effect <= 1e-20 |1 - 1/dt| / tun).
+// out: [rows_out, ldo] fp32, rows >= K and columns past the operand are zero.  One CTA per row.
+__global__ void emission_prepare_aug_kernel(int K, int N, const float* __restrict__ tuning,
+                                            const float* __restrict__ ma_neuron, float dt, int mode,
+                                            float* __restrict__ out, int64_t ldo, float* __restrict__ lam_sum) {
+  const int k = blockIdx.x;
+  float* o = out + (size_t)k * ldo;
+  if (k >= K) {
+    for (int n = threadIdx.x; n < (int)ldo; n += blockDim.x) o[n] = 0.f;
+    return;
+  }
+  const int ncol = mode == 1 ? 2 * N : N + 1;
+  double acc = 0.0, msum = 0.0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float tun = tuning[(size_t)k * N + n];
+    if (mode == 1) {
+      const float lam = tun * dt + kLamFloor;
+      o[n] = logf(lam);
+      o[N + n] = -lam;
+    } else {
+      const float m = ma_neuron ? ma_neuron[n] : 1.f;
+      o[n] = m * logf(tun + kLamFloor);
+      acc += (double)(m * tun);
+      msum += (double)m;
+    }
+  }
+  for (int n = ncol + threadIdx.x; n < (int)ldo; n += blockDim.x) o[n] = 0.f;
+  acc = warp_sum_d(acc);
+  msum = warp_sum_d(msum);
+  __shared__ double sm[2][32];
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = acc; sm[1][threadIdx.x >> 5] = msum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, ms = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += sm[0][w]; ms += sm[1][w]; }
+    if (mode == 1) {
+      lam_sum[k] = 0.f;
+    } else {
+      o[N] = -(float)s;
+      lam_sum[k] = (float)(ms * (double)kLamFloor);
+    }
+  }
 }
 
 // ---- CUDA-core fp32 tile GEMM with the emission epilogue: used when the counts are not exactly
@@ -152,8 +212,27 @@ extern "C" int pmg_emission_prepare(int K, int N, const float* tuning, const flo
 
 extern "C" int pmg_emission_lgamma_rowsum(int64_t T, int N, const float* y, int64_t ldy,
                                           const float* ma_neuron, float* lgam, pmg_stream_t stream) {
+  return pmg_emission_row_terms(T, N, y, ldy, ma_neuron, 0, lgam, nullptr, stream);
+}
+
+extern "C" int pmg_emission_row_terms(int64_t T, int N, const float* y, int64_t ldy, const float* ma_neuron,
+                                      int64_t ld_mask, float* lgam, float* ysum, pmg_stream_t stream) {
   if (T <= 0 || N <= 0 || !y || !lgam || ldy < N) return PMG_ERR_BAD_ARG;
-  pmg::lgamma_rowsum_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, N, y, ldy, ma_neuron, lgam);
+  if (ma_neuron && ld_mask != 0 && ld_mask < N) return PMG_ERR_BAD_ARG;
+  pmg::lgamma_rowsum_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, N, y, ldy, ma_neuron, ld_mask,
+                                                                              lgam, ysum);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_emission_prepare_aug(int K, int N, const float* tuning, const float* ma_neuron, float dt,
+                                        int mode, int rows_out, float* out, int64_t ldo, float* lam_sum,
+                                        pmg_stream_t stream) {
+  if (K <= 0 || N <= 0 || !tuning || !out || !lam_sum || rows_out < K) return PMG_ERR_BAD_ARG;
+  if (mode != 1 && mode != 2) return PMG_ERR_BAD_ARG;
+  if (ldo < (mode == 1 ? 2 * (int64_t)N : (int64_t)N + 1)) return PMG_ERR_BAD_ARG;
+  pmg::emission_prepare_aug_kernel<<<rows_out, 128, 0, (cudaStream_t)stream>>>(K, N, tuning, ma_neuron, dt, mode,
+                                                                              out, ldo, lam_sum);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

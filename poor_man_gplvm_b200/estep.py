@@ -72,8 +72,17 @@ class EStep:
         S = self.plan.n_chain
         self.S = S
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.lgam = ops.lgamma_rowsum(self.y, ma_neuron)
-        self.y16 = ops.CountsF16(self.y) if emission_impl == 0 else None
+        # emission operands (constant across EM iterations); a [T,N] neuron mask arrives for the core bins
+        # only, so the neighbours' halo rows of the mask are exchanged like the halo rows of y
+        if ma_neuron is not None and ma_neuron.dim() == 2:
+            ma_neuron, _, _ = self.shard.halo_exchange(ma_neuron.contiguous(), self.halo)
+            self.ma_neuron = ma_neuron
+        self.em = ops.EmissionOperands(self.y, ma_neuron, impl=emission_impl)
+        # fp16 counts for the statistics GEMM (the M-step uses the unmasked counts, reference core.py:807)
+        if self.em.mode == 0:
+            self.y16 = self.em.A16
+        else:
+            self.y16 = ops.CountsF16(self.y) if emission_impl == 0 else None
         self.ll = torch.empty((self.T, self.K), **f32)
         self.alpha = torch.zeros((self.T, 2, self.K), **f32)
         self.lmr = torch.zeros(self.T, **f32)
@@ -108,8 +117,7 @@ class EStep:
 
     # -- pieces ---------------------------------------------------------------------------
     def emission(self, tuning):
-        ops.emission(self.y, tuning, self.lgam, self.ma_neuron, self.ma_latent, 1.0, out=self.ll, y16=self.y16,
-                     impl=self.emission_impl)
+        self.em.loglik(tuning, self.ma_latent, 1.0, out=self.ll)
         return self.ll
 
     def _exchange_fwd(self):

@@ -67,15 +67,26 @@ def emission_prepare(tuning, ma_neuron=None, dt=1.0):
     return loglam, lam_sum
 
 
-def lgamma_rowsum(y, ma_neuron=None):
+def lgamma_rowsum(y, ma_neuron=None, want_ysum=False):
+    """lgam[t] = sum_n m lgamma(y+1) (and optionally ysum[t] = sum_n m y); m: None, [N] or [T,N]."""
     lib = _lib.load()
     _f32(y, "y", 2)
     T, N = y.shape
     out = torch.empty(T, dtype=torch.float32, device=y.device)
-    check(lib.pmg_emission_lgamma_rowsum(T, N, _p(y), N, _p(ma_neuron), _p(out), _stream()),
-          "pmg_emission_lgamma_rowsum")
+    ysum = torch.empty(T, dtype=torch.float32, device=y.device) if want_ysum else None
+    ldm = 0
+    if ma_neuron is not None:
+        _f32(ma_neuron, "ma_neuron")
+        if ma_neuron.dim() == 2:
+            if tuple(ma_neuron.shape) != (T, N):
+                raise ValueError("ma_neuron must be [N] or [T,N]")
+            ldm = N
+        elif ma_neuron.shape[0] != N:
+            raise ValueError("ma_neuron must be [N] or [T,N]")
+    check(lib.pmg_emission_row_terms(T, N, _p(y), N, _p(ma_neuron), ldm, _p(out), _p(ysum), _stream()),
+          "pmg_emission_row_terms")
     _count(1)
-    return out
+    return (out, ysum) if want_ysum else out
 
 
 def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None):
@@ -157,6 +168,83 @@ def emission(y, tuning, lgam, ma_neuron=None, ma_latent=None, dt=1.0, out=None, 
         return emission_poisson_f16(y16, L16, lam_sum, lgam, tuning.shape[0], ma_latent, out=out)
     loglam, lam_sum = emission_prepare(tuning, ma_neuron, dt)
     return emission_poisson(y, loglam, lam_sum, lgam, ma_latent, out=out)
+
+
+def emission_prepare_aug(tuning, mode, ma_neuron=None, dt=1.0, rows_out=None):
+    """Augmented right-hand operand (see pmg_emission_prepare_aug): mode 1 = [T,N] neuron mask,
+    mode 2 = per-bin dt.  Returns (B_aug [rows_out, N_aug] fp32, lam_sum [K])."""
+    lib = _lib.load()
+    _f32(tuning, "tuning", 2)
+    K, N = tuning.shape
+    n_aug = 2 * N if mode == 1 else N + 1
+    rows = K if rows_out is None else int(rows_out)
+    B = torch.empty((rows, n_aug), dtype=torch.float32, device=tuning.device)
+    lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
+    check(lib.pmg_emission_prepare_aug(K, N, _p(tuning), _p(ma_neuron), float(dt), int(mode), rows, _p(B), n_aug,
+                                       _p(lam_sum), _stream()), "pmg_emission_prepare_aug")
+    _count(1)
+    return B, lam_sum
+
+
+class EmissionOperands:
+    """Left-hand operand and row terms of the emission GEMM for one recording (constant across EM
+    iterations), covering the reference's whole mask surface:
+      * ma_neuron None / [N]   : A = y, the mask is folded into the right-hand operand (decoder.py:43);
+      * ma_neuron [T,N]        : A = [m*y | m] against [log lam | -lam]            (decoder.py:291-294);
+      * dt_l [T] (naive Bayes) : A = [y | dt_t] against [ma log(tun+1e-20) | -sum ma tun], the row term
+                                 gains -log(dt_t) sum_n ma y                        (decoder.py:73-85).
+    The fp16 tensor-core kernel is used whenever A is exact in fp16 (integer counts <= 2048 and 0/1 masks);
+    otherwise the fp32 CUDA-core tiles."""
+
+    def __init__(self, y, ma_neuron=None, dt_l=None, impl=0):
+        _f32(y, "y", 2)
+        self.T, self.N = y.shape
+        self.mode = 0
+        self.ma_vec = None
+        self.per_bin_dt = dt_l is not None
+        if ma_neuron is not None and ma_neuron.dim() == 2:
+            self.mode = 1
+            if dt_l is None:
+                self.A = torch.cat([y * ma_neuron, ma_neuron], dim=1).contiguous()
+                self.lgam = lgamma_rowsum(y, ma_neuron)
+            else:
+                # both options: A = [m*y | dt_t*m] against [log(tun+1e-20) | -(tun+1e-20)] (mode-1 operand at dt=1)
+                self.A = torch.cat([y * ma_neuron, ma_neuron * dt_l.reshape(-1, 1)], dim=1).contiguous()
+                lgam, ysum = lgamma_rowsum(y, ma_neuron, want_ysum=True)
+                self.lgam = lgam - torch.log(dt_l) * ysum
+        elif dt_l is not None:
+            self.mode = 2
+            self.ma_vec = ma_neuron
+            self.A = torch.cat([y, dt_l.reshape(-1, 1)], dim=1).contiguous()
+            lgam, ysum = lgamma_rowsum(y, ma_neuron, want_ysum=True)
+            self.lgam = lgam - torch.log(dt_l) * ysum
+        else:
+            self.ma_vec = ma_neuron
+            self.A = y
+            self.lgam = lgamma_rowsum(y, ma_neuron)
+        # per-bin dt is not fp16-exact: that path always runs on the fp32 tiles
+        self.A16 = CountsF16(self.A) if (impl == 0 and not self.per_bin_dt) else None
+
+    @property
+    def tensor_cores(self):
+        return self.A16 is not None and self.A16.exact
+
+    def loglik(self, tuning, ma_latent=None, dt=1.0, out=None):
+        """ll[T,K] for this recording under `tuning` [K,N]."""
+        K = tuning.shape[0]
+        if self.per_bin_dt:
+            dt = 1.0                      # dt_t lives in the left-hand operand and the row term
+        if self.mode == 0:
+            return emission(self.A, tuning, self.lgam, self.ma_vec, ma_latent, dt, out=out, y16=self.A16,
+                            impl=0 if self.tensor_cores else 1)
+        if self.tensor_cores:
+            bn = emission_tile_n(K)
+            Kpad = (K + bn - 1) // bn * bn
+            B, lam_sum = emission_prepare_aug(tuning, self.mode, self.ma_vec, dt, rows_out=Kpad)
+            L16 = split_f16(B, out=torch.empty((2, Kpad, self.A16.ld), dtype=torch.float16, device=B.device))
+            return emission_poisson_f16(self.A16, L16, lam_sum, self.lgam, K, ma_latent, out=out)
+        B, lam_sum = emission_prepare_aug(tuning, self.mode, self.ma_vec, dt)
+        return emission_poisson(self.A, B, lam_sum, self.lgam, ma_latent, out=out)
 
 
 def naive_bayes_normalize(ll, inplace=False):
