@@ -14,6 +14,7 @@
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
 #include "pmg_common.cuh"
 #include "pmg_tc.cuh"
+#include <cstdlib>
 
 namespace pmg {
 
@@ -230,7 +231,10 @@ static uint32_t pow2_cols(int c) {
 // BN = accumulator columns per tile: K split into ceil(K/256) tiles, rounded up to 16
 extern "C" int pmg_emission_tile_n(int K) {
   if (K <= 0) return 0;
-  const int nt = (K + 255) / 256;
+  int nt = (K + 255) / 256;
+  // experiment knob: more, narrower column tiles (smaller pipeline stages)
+  static const int nt_env = std::getenv("PMG_EM_NT") ? std::atoi(std::getenv("PMG_EM_NT")) : 0;
+  if (nt_env > nt) nt = nt_env;
   int bn = (K + nt - 1) / nt;
   bn = (bn + 15) / 16 * 16;
   return bn;
@@ -280,8 +284,11 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   p.n_mtiles = (int)((T + TC_BM - 1) / TC_BM);
   p.n_ntiles = n_ntiles;
   const uint32_t stage_bytes = TC_A_BYTES + EM_PB * BN * TC_BK * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > 6) stages = 6;
+  // 227 KB of shared memory per CTA minus alignment slack and barriers
+  int stages = (int)((225 * 1024) / stage_bytes);
+  static const int st_env = std::getenv("PMG_EM_STAGES") ? std::atoi(std::getenv("PMG_EM_STAGES")) : 0;
+  if (st_env > 0 && stages > st_env) stages = st_env;
+  if (stages > 8) stages = 8;
   if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
   p.stages = stages;
   p.idesc = make_idesc_f16(TC_BM, BN, 0, 0, 0);

@@ -70,17 +70,22 @@ def test_fit_em_readme_config_pinned_adam():
 
 
 def test_fit_em_readme_config_default_adam():
-    """Same model with the reference's default optimiser (maxiter=1000, tol=1e-6, data-dependent stop)."""
+    """Same model with the reference's default optimiser (maxiter=1000, tol=1e-6).  The stopping step is decided
+    by a relative loss change of 1e-6, i.e. by rounding: the reference source itself stops at
+    [1000, 548, 553, 314, 134] steps in fp64 and [1000, 524, 499, 310, 134] in fp32, and its fp32 and fp64 runs
+    differ by 1.7e-2 (tuning, relative) / 5e-3 (posterior) / 6e-5 (log marginal).  The CUDA path must stay
+    within that spread of the fp64 run (and within the nominal tolerance where the spread is smaller)."""
     g, c = load("readme_default")
+    g32, _ = load("readme_default", "f32")
     m = make_model(g, c)
     got = m.fit_em(g["in_y"].astype(np.float32), **em_kwargs(g, c))
     lw, lg = g["em_log_marginal_l"], np.array(got["log_marginal_l"], dtype=np.float64)
     assert np.max(np.abs(lg - lw) / np.abs(lw)) < 1e-4
-    assert np.max(np.abs(got["tuning"] - g["em_tuning"]) / g["em_tuning"]) < 1e-3
-    assert np.max(np.abs(got["posterior"] - g["em_posterior"])) < 1e-4
-    # the stopping step is decided by a relative loss change of 1e-6, i.e. by rounding: the reference source
-    # itself stops at [1000, 548, 553, 314, 134] in fp64 and [1000, 524, 499, 310, 134] in fp32
-    n64, n32 = g["em_m_n_iter"], load("readme_default", "f32")[0]["em_m_n_iter"]
+    spread_t = np.max(np.abs(g32["em_tuning"] - g["em_tuning"]) / g["em_tuning"])
+    spread_p = np.max(np.abs(g32["em_posterior"].astype(np.float64) - g["em_posterior"]))
+    assert np.max(np.abs(got["tuning"] - g["em_tuning"]) / g["em_tuning"]) < max(1e-3, spread_t)
+    assert np.max(np.abs(got["posterior"] - g["em_posterior"])) < max(1e-5, spread_p)
+    n64, n32 = g["em_m_n_iter"], g32["em_m_n_iter"]
     n_got = np.array(got["m_step_res_l"]["n_iter"])
     lo, hi = np.minimum(n64, n32), np.maximum(n64, n32)
     assert np.all(n_got >= 0.85 * lo) and np.all(n_got <= 1.15 * hi), (n64, n32, n_got)
