@@ -301,10 +301,10 @@ def run_ours(args):
     if not args.no_e2e:
         n_iter = args.e2e_iters
         y_host = y_dev.cpu().numpy()
-        lp_host, _ = model.init_latent_posterior(T, key=5)
         barrier()
         t0 = time.perf_counter()
-        em = model.fit_em(y_host, n_iter=n_iter, log_posterior_init=lp_host, m_step_maxiter=args.m_step_maxiter,
+        # the README call: fit_em(y, n_iter=20) with the default random initial posterior (drawn from `key`)
+        em = model.fit_em(y_host, key=5, n_iter=n_iter, m_step_maxiter=args.m_step_maxiter,
                           m_step_tol=args.m_step_tol, time_sharded=world > 1)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0

@@ -147,6 +147,26 @@ int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const floa
  * est/truth are [n, len] with row strides in elements (truth rows may live inside alpha). */
 int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, const float* truth,
                    int64_t ld_truth, float floor_val, float* err, pmg_stream_t stream);
+/* EM-iteration fast path of the two passes ("compact" filtered posterior).  The filtered jump-state
+ * message is a scalar multiple of the likelihood factor, alpha_t[1,x] = a1s_t * exp2(s*log2e*(ll[t,x] -
+ * max_x ll[t,:])), so the forward pass stores ax[T, ldax] with columns 0..K-1 = alpha_t[0,:], column K =
+ * a1s_t, column K+1 = lmr_t (ldax >= K+4, ldax % 4 == 0) and the backward pass rebuilds alpha_t[1,:] from
+ * the ll row; it emits only what an EM iteration consumes (gamma16; sum_t gamma comes out of the statistics
+ * GEMM through a column of ones appended to the counts) plus the seam messages.
+ * Supported: kind 0 (Toeplitz), W <= 10, K % 8 == 0, K <= 496, M[0] > 0, likelihood_scale > 0
+ * (pmg_scan_compact_supported); everything else uses pmg_forward / pmg_backward.
+ * fwd_end: [n_chain,2,K] true message at the last bin of each chain; first_out: [2,K] true message at
+ * core_begin; mode 1 restarts the listed chains from warm_in (a snapshot of their carry). */
+int pmg_scan_compact_supported(const pmg_transition* tr, float likelihood_scale);
+int pmg_forward_compact(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                        const float* carry_in, const float* warm_in, int64_t warm_stride, float* warm_out,
+                        float* ax, int64_t ldax, float* halo_state, float* fwd_end, float* first_out,
+                        int mode, const int* chain_ids, int n_ids, pmg_stream_t stream);
+int pmg_backward_compact(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                         const float* ax, int64_t ldax, const float* beta_in, const float* warm_in,
+                         int64_t warm_stride, float* warm_out, void* gamma16, int64_t ldg,
+                         float* beta_halo, float* beta_end, int mode, const int* chain_ids, int n_ids,
+                         pmg_stream_t stream);
 
 /* ------------------------------------------------------------------ M1, S4 --
  * C[m,n] = sum_t A[t,m]*B[t,n]  (time is the reduction axis).  Used for the
@@ -193,6 +213,16 @@ int pmg_mstep_adam(int K, int B, int N, const float* Phi, const float* yw, const
 /* tuning[k,n] = softplus(sum_b Phi[k,b]*W[b,n])   (fit_tuning_helper.py:11-25) */
 int pmg_tuning_softplus(int K, int B, int N, const float* Phi, const float* W, float* tuning,
                         pmg_stream_t stream);
+
+/* ---------------------------------------------------------------------- D2 --
+ * Initial latent posterior, core.py:571-583, with jax.random's bit stream (threefry2x32, jax 0.4.26 defaults):
+ * rows [t_offset, t_offset+T) of uniform(key, (T_total, K)) * random_scale, row-normalised.  Any of the outputs
+ * may be NULL: post [T, ldp] fp32, logpost [T, ldl] fp32, g16 = fp16 hi/lo pieces (hi at g16, lo at
+ * g16 + piece_stride halves, row stride ldg), tw [K] fp64 = column sums of post (zeroed by the callee).
+ * Requires T_total*K < 2^32 (one counter block of the reference's generator). */
+int pmg_threefry_posterior_init(int64_t T, int K, int64_t t_offset, int64_t T_total, uint32_t key0, uint32_t key1,
+                                float random_scale, float* post, int64_t ldp, float* logpost, int64_t ldl,
+                                void* g16, int64_t ldg, int64_t piece_stride, double* tw, pmg_stream_t stream);
 
 #ifdef __cplusplus
 }

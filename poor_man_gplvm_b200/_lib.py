@@ -56,6 +56,13 @@ SIGNATURES = {
     "pmg_backward": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
                                c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                C.c_int, c_i32p, C.c_int, c_stream]),
+    "pmg_scan_compact_supported": (C.c_int, [C.POINTER(PmgTransition), C.c_float]),
+    "pmg_forward_compact": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
+                                      c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int,
+                                      c_i32p, C.c_int, c_stream]),
+    "pmg_backward_compact": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
+                                       C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_void_p, C.c_int64,
+                                       c_f32p, c_f32p, C.c_int, c_i32p, C.c_int, c_stream]),
     "pmg_split_f16": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, C.c_void_p, C.c_int64, c_stream]),
     "pmg_atb_f16_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "pmg_atb_f16": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_f32p,
@@ -71,6 +78,9 @@ SIGNATURES = {
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, c_f32p, c_f32p,
                                  c_f32p, c_i32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_void_p, C.c_int64,
                                  c_stream]),
+    "pmg_threefry_posterior_init": (C.c_int, [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
+                                              C.c_float, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.c_int64, C.c_void_p, c_stream]),
     "pmg_tuning_softplus": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
 }
 

@@ -18,6 +18,7 @@ import torch
 
 from . import gp_kernel as gpk
 from . import hostio
+from . import jaxprng
 from . import ops
 from .estep import EStep
 from .shard import TimeShard
@@ -61,10 +62,15 @@ class _Timing:
 
 
 def _seed_from_key(key):
+    """seed for the NumPy generators of sample* (jax.random.poisson / choice are not restated)"""
     if key is None:
         return 0
     a = np.asarray(key).astype(np.uint64).ravel()
     return int(a[-1]) if a.size else 0
+
+
+# above this many entries the initial posterior is drawn on the device (pmg_threefry_posterior_init)
+_HOST_PRNG_MAX = 1 << 22
 
 
 def compute_transition_posterior_prob(log_acc):
@@ -97,7 +103,9 @@ class EMLoop:
     ``fit_em``: statistics -> Adam M-step -> tuning -> E-step."""
 
     def __init__(self, model, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
-                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None, shard=None):
+                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None, shard=None, posterior_key=None):
+        """log_posterior_init: [T,K] array, or None with posterior_key = (key, random_scale, t_offset, T_total):
+        the reference's random initial posterior (core.py:571-583) drawn on the device."""
         self.y = y_dev
         self.Phi = model._dev(tuning_basis)
         self.W = model._dev(model.params).clone()
@@ -106,27 +114,37 @@ class EMLoop:
         self.state = ops.AdamState(self.W)
         self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len, shard=shard)
         self.shard = self.es.shard
-        gamma_lat = torch.exp(model._dev(log_posterior_init))
-        if gamma_lat.shape != (y_dev.shape[0], op.K):
-            raise ValueError("log_posterior_init must be [T, n_latent_bin]")
-        self.tw = gamma_lat.sum(dim=0, dtype=torch.float64).to(torch.float32)
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
         self.use_tc = self.es.y16 is not None and self.es.y16.exact
-        if self.use_tc:
-            # pieces live on the rank's extended block (core + neighbour halos); halo rows stay zero, so
-            # the time reduction over the extended block only counts this rank's own bins
-            self.gamma16 = ops.new_gamma16(self.es.T, op.K, y_dev.device)
-            self.gamma16[:, self.es.core] = ops.split_f16(gamma_lat)
-            self.gamma_lat = None
+        T_core, K = y_dev.shape[0], op.K
+        # fp16 pieces live on the rank's extended block (core + neighbour halos); halo rows stay zero, so
+        # the time reduction over the extended block only counts this rank's own bins
+        self.gamma16 = ops.new_gamma16(self.es.T, K, y_dev.device) if self.use_tc else None
+        self.gamma_lat, self.tw = None, None
+        if log_posterior_init is None:
+            key, random_scale, t_offset, T_total = posterior_key
+            post, _, tw = ops.threefry_posterior_init(T_core, K, key, random_scale, y_dev.device, t_offset, T_total,
+                                                      want_post=not self.use_tc, g16=self.gamma16,
+                                                      g16_row0=self.es.core.start, want_tw=not self.use_tc)
+            self.gamma_lat, self.tw = post, tw
         else:
-            self.gamma16 = None
-            self.gamma_lat = gamma_lat
+            gamma_lat = torch.exp(model._dev(log_posterior_init))
+            if gamma_lat.shape != (T_core, K):
+                raise ValueError("log_posterior_init must be [T, n_latent_bin]")
+            if self.use_tc:
+                self.gamma16[:, self.es.core] = ops.split_f16(gamma_lat)
+            else:
+                self.gamma_lat = gamma_lat
+                self.tw = gamma_lat.sum(dim=0, dtype=torch.float64).to(torch.float32)
 
     def iteration(self, want_gamma=False, want_dyn=False, want_gamma_lat=False):
         """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path)."""
         if self.use_tc:
-            yw = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)  # reference core.py:807
+            # reference core.py:807; the ones column of the fp16 counts makes column N = sum_t gamma
+            stats = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)
+            N = self.es.y16.N
+            yw, self.tw = stats[:, :N].contiguous(), stats[:, N].contiguous()
         else:
             yw = ops.atb(self.gamma_lat, self.y)
         self.shard.allreduce_sum_(yw, self.tw)                      # time-sharded ranks: one packed all-reduce
@@ -136,7 +154,9 @@ class EMLoop:
         ops.phase("mstep")
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16)
-        self.gamma_lat, self.tw = res.gamma_lat, res.tw            # reference core.py:668
+        self.gamma_lat = res.gamma_lat                             # reference core.py:668
+        if res.tw is not None:
+            self.tw = res.tw
         if self.shard.active:
             lm = res.log_marginal.reshape(1)
             self.shard.allreduce_sum_(lm)
@@ -171,7 +191,7 @@ class PoissonGPLVMJump1D:
         self.p_jump_to_move = p_jump_to_move
         self.explained_variance_threshold_basis = explained_variance_threshold_basis
         self.rng_init_int = rng_init_int
-        self.rng_init = rng_init_int
+        self.rng_init = jaxprng.PRNGKey(rng_init_int)
         self.n_neuron = n_neuron
         self.possible_latent_bin = np.arange(n_latent_bin)
         self.possible_dynamics = np.arange(2)
@@ -227,24 +247,28 @@ class PoissonGPLVMJump1D:
         return self._host(ops.tuning_softplus(Phi, W))
 
     def initialize_params(self, key):
-        """reference core.py:429-437.  NOTE: NumPy PRNG, not JAX threefry: set
-        ``model.params`` explicitly for key-for-key reproduction of a reference run."""
-        rng = np.random.default_rng(_seed_from_key(key))
-        params = (rng.standard_normal((self.n_basis, self.n_neuron)) * np.sqrt(self.w_init_variance)
-                  + self.w_init_mean).astype(np.float32)
+        """reference core.py:429-437: normal(key, (n_basis, n_neuron)) * sqrt(w_init_variance) + w_init_mean with
+        jax.random's bit stream (jaxprng.py).  (The tuning basis comes from an SVD whose sign convention is
+        backend dependent in the reference as well; inject ``tuning_basis`` for run-for-run reproduction.)"""
+        params = (jaxprng.normal(key, (self.n_basis, self.n_neuron)) * np.float32(np.sqrt(self.w_init_variance))
+                  + np.float32(self.w_init_mean)).astype(np.float32)
         self.params = params
         # softplus(Phi W) on the host: the constructor must work without touching the GPU
         self.tuning = np.logaddexp(self.tuning_basis @ params, np.float32(0)).astype(np.float32)
         return self.params, self.tuning
 
     def init_latent_posterior(self, T, key, random_scale=0.1):
-        """reference core.py:571-583 (NumPy PRNG stream)."""
-        rng = np.random.default_rng(_seed_from_key(key))
-        posterior = (rng.random((T, self.n_latent_bin), dtype=np.float32) * np.float32(random_scale))
+        """reference core.py:571-583 with jax.random's bit stream: uniform(key, (T, K)) * random_scale, row
+        normalised.  Returns (log_posterior, posterior) as NumPy arrays; large draws run on the device."""
+        K = self.n_latent_bin
+        if T * K > _HOST_PRNG_MAX and torch.cuda.is_available():
+            post, logp, _ = ops.threefry_posterior_init(T, K, key, random_scale, self.device, want_post=True,
+                                                        want_log=True)
+            return self._host(logp), self._host(post)
+        posterior = jaxprng.uniform(key, (T, K)) * np.float32(random_scale)
         posterior = posterior / posterior.sum(axis=1, keepdims=True)
         with np.errstate(divide="ignore"):
-            log_posterior = np.log(posterior)
-        log_posterior = np.where(np.isneginf(log_posterior), np.float32(-np.inf), log_posterior)
+            log_posterior = np.log(posterior)            # log(0) = -inf, the reference's -1e40 in fp32
         return log_posterior, posterior
 
     def _transition_pack(self, hyperparam):
@@ -430,10 +454,24 @@ class PoissonGPLVMJump1D:
                                               include_bias=True)
         else:
             tuning_basis = self.tuning_basis
+        shard = TimeShard(group) if time_sharded else None
+        posterior_key = None
         if log_posterior_init is None:
-            log_posterior_init, _ = self.init_latent_posterior(T, key, **posterior_init_kwargs)
-        loop = EMLoop(self, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
-                      m_step_step_size, m_step_maxiter, m_step_tol, shard=TimeShard(group) if time_sharded else None)
+            # the reference draws uniform(key, (T, K)) on its device (core.py:579); here the same bit stream is
+            # generated on the GPU straight into the operands of the first M-step; em_res['log_posterior_init']
+            # regenerates it on demand.  A time-sharded rank draws its rows of the global [T_total, K] array.
+            random_scale = posterior_init_kwargs.get('random_scale', 0.1)
+            t_offset, T_total = (shard.block_offset(T) if shard is not None else (0, T))
+            posterior_key = (jaxprng.as_key(key), random_scale, t_offset, T_total)
+            dev_ = self.device
+            log_posterior_init = hostio.LazyHostArray(
+                None, shape=(T, K), producer=lambda: ops.threefry_posterior_init(
+                    T, K, posterior_key[0], random_scale, dev_, t_offset, T_total, want_log=True)[1])
+            loop_init = None
+        else:
+            loop_init = log_posterior_init
+        loop = EMLoop(self, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, loop_init, prior_std,
+                      m_step_step_size, m_step_maxiter, m_step_tol, shard=shard, posterior_key=posterior_key)
         self.opt_state_init_fun = ops.AdamState
         W, state, es = loop.W, loop.state, loop.es
         tm.mark("setup")

@@ -820,3 +820,5 @@ extern "C" int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, 
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }
+
+#include "pmg_scan_pk.cuh"

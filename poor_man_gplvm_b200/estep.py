@@ -23,7 +23,7 @@ from .shard import TimeShard
 
 DEFAULT_HALO = int(os.environ.get("PMG_HALO", "256"))
 DEFAULT_SEAM_TOL = float(os.environ.get("PMG_SEAM_TOL", "1e-5"))
-MIN_CHUNK_OVER_HALO = int(os.environ.get("PMG_MIN_CHUNK_OVER_HALO", "4"))
+MIN_CHUNK_OVER_HALO = int(os.environ.get("PMG_MIN_CHUNK_OVER_HALO", "3"))
 
 
 def plan_chunks(n_core, halo, sm_count, chains_per_sm=8):
@@ -77,15 +77,20 @@ class EStep:
         if ma_neuron is not None and ma_neuron.dim() == 2:
             ma_neuron, _, _ = self.shard.halo_exchange(ma_neuron.contiguous(), self.halo)
             self.ma_neuron = ma_neuron
-        self.em = ops.EmissionOperands(self.y, ma_neuron, impl=emission_impl)
+        self.em = ops.EmissionOperands(self.y, ma_neuron, impl=emission_impl, ones_col=True)
         # fp16 counts for the statistics GEMM (the M-step uses the unmasked counts, reference core.py:807)
         if self.em.mode == 0:
             self.y16 = self.em.A16
         else:
-            self.y16 = ops.CountsF16(self.y) if emission_impl == 0 else None
+            self.y16 = ops.CountsF16(self.y, ones_col=True) if emission_impl == 0 else None
         self.ll = torch.empty((self.T, self.K), **f32)
-        self.alpha = torch.zeros((self.T, 2, self.K), **f32)
+        self._alpha = None                 # [T,2,K] filtered posterior of the general path (allocated on first use)
+        self._ax = None                    # [T,K+4] compact filtered posterior of the EM fast path
         self.lmr = torch.zeros(self.T, **f32)
+        self.compact_ok = (os.environ.get("PMG_SCAN_COMPACT", "1") != "0"
+                           and ops.scan_compact_supported(op, self.scale))
+        self.fwd_end = torch.zeros((S, 2, self.K), **f32)       # true message at the last bin of each chain
+        self.first_out = torch.zeros((2, self.K), **f32)        # true message at the first core bin
         self.halo_state = torch.zeros((S, 2, self.K), **f32)
         self.beta_halo = torch.zeros((S, 2, self.K), **f32)
         self.beta_end = torch.zeros((S + 1, 2, self.K), **f32)     # [S] = the right neighbour's first chain
@@ -115,23 +120,47 @@ class EStep:
         self.f_lo = 0 if not self.shard.is_first else 1
         self.b_hi = S if not self.shard.is_last else S - 1
 
+    @property
+    def alpha(self):
+        if self._alpha is None:
+            self._alpha = torch.zeros((self.T, 2, self.K), dtype=torch.float32, device=self.dev)
+        return self._alpha
+
+    @property
+    def ax(self):
+        if self._ax is None:
+            self._ax = torch.zeros((self.T, self.K + 4), dtype=torch.float32, device=self.dev)
+        return self._ax
+
     # -- pieces ---------------------------------------------------------------------------
     def emission(self, tuning):
         self.em.loglik(tuning, self.ma_latent, 1.0, out=self.ll)
         return self.ll
 
-    def _exchange_fwd(self):
+    def _exchange_fwd(self, compact=False):
         """After a forward pass: the last true alpha goes right (seam truth of the neighbour's first
         chain), the first true alpha goes left (normaliser of the neighbour's last backward seam)."""
         if not self.shard.active:
             return
-        first = self.alpha[self.core.start].reshape(-1)
-        last = self.alpha[self.core.stop - 1].reshape(-1)
+        if compact:
+            first, last = self.first_out.reshape(-1), self.fwd_end[self.S - 1].reshape(-1)
+        else:
+            first = self.alpha[self.core.start].reshape(-1)
+            last = self.alpha[self.core.stop - 1].reshape(-1)
         from_left, from_right = self.shard.boundary(first, last)
         if from_left is not None:
             self.truth_left = from_left.view(2, self.K)
         if from_right is not None:
-            self.alpha[self.core.stop].copy_(from_right.view(2, self.K))
+            msg = from_right.view(2, self.K)
+            if compact:
+                # row of the compact buffer for the neighbour's first bin: alpha[0,:] and the scalar a1s with
+                # alpha[1,x] = a1s * exp2(s*log2e*(ll[x] - max ll))  (the factor the kernels recompute)
+                row = self.ll[self.core.stop]
+                E = torch.exp2((row - row.max()) * (self.scale * 1.4426950408889634))
+                self.ax[self.core.stop, :self.K] = msg[0]
+                self.ax[self.core.stop, self.K] = msg[1].sum() / E.sum()
+            else:
+                self.alpha[self.core.stop].copy_(msg)
 
     def _exchange_bwd(self):
         """After a backward pass: beta at the first core bin goes left (seam truth of the neighbour's last chain)."""
@@ -141,10 +170,10 @@ class EStep:
         if from_right is not None:
             self.beta_end[self.S].copy_(from_right.view(2, self.K))
 
-    def _check_fwd(self):
+    def _check_fwd(self, compact=False):
         S, K2 = self.S, 2 * self.K
         if S > 1:
-            self.truth[1:] = self.alpha[self.rows_f]
+            self.truth[1:] = self.fwd_end[:-1] if compact else self.alpha[self.rows_f]
         if self.f_lo == 0:
             self.truth[0] = self.truth_left
         n = S - self.f_lo
@@ -169,6 +198,9 @@ class EStep:
         the hi/lo pieces of the latent posterior."""
         S, K = self.S, self.K
         f32 = dict(dtype=torch.float32, device=self.dev)
+        # EM fast path: only the fp16 posterior pieces and sum_t gamma are wanted -> compact kernels
+        compact = (self.compact_ok and gamma16 is not None
+                   and not (want_gamma or want_gamma_lat or want_dyn or want_r))
         self.emission(tuning)
         ops.phase("emission")
         gamma = torch.empty((self.T, 2, K), **f32) if want_gamma else None
@@ -181,19 +213,29 @@ class EStep:
         b_in = self.bwarm[cur] if self.warm_valid else None
 
         def fwd(mode=0, ids=None):
+            if compact:
+                ops.forward_compact(self.plan, self.op, self.ll, self.ax,
+                                    halo_state=(self.halo_state if mode == 0 else None), fwd_end=self.fwd_end,
+                                    first_out=self.first_out, mode=mode, chain_ids=ids,
+                                    warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt])
+                return
             ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr,
                         halo_state=(self.halo_state if mode == 0 else None), mode=mode, chain_ids=ids,
                         warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt])
 
         def bwd(mode=0, ids=None):
+            if compact:
+                ops.backward_compact(self.plan, self.op, self.ll, self.ax, gamma16, beta_halo=self.beta_halo, beta_end=self.beta_end, mode=mode, chain_ids=ids,
+                                     warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=self.bwarm[nxt])
+                return
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
                          mode=mode, chain_ids=ids, gamma16=gamma16,
                          warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=self.bwarm[nxt])
 
         fwd()
-        self._exchange_fwd()
-        self._check_fwd()
+        self._exchange_fwd(compact)
+        self._check_fwd(compact)
         ops.phase("forward")
         bwd()
         self._exchange_bwd()
@@ -221,8 +263,8 @@ class EStep:
                     ids = bad.to(device=self.dev, dtype=torch.int32)
                     self.halo_state[ids.long()] = self.truth[ids.long()]      # carry snapshot = new "estimate"
                     fwd(mode=1, ids=ids)
-                self._exchange_fwd()
-                self._check_fwd()
+                self._exchange_fwd(compact)
+                self._check_fwd(compact)
                 ef = self._read_err()[self.f_lo:S].clone()
             if redo_bwd:
                 bwd()
@@ -246,15 +288,18 @@ class EStep:
         c = self.core
         res = EStepResult()
         res.core = c
-        res.ll, res.alpha, res.lmr = self.ll[c], self.alpha[c], self.lmr[c]
-        res.alpha_ext, res.r_ext = self.alpha, r
+        lmr = self.ax[:, K + 1] if compact else self.lmr
+        res.ll, res.lmr = self.ll[c], lmr[c]
+        res.alpha = None if compact else self.alpha[c]
+        res.alpha_ext, res.r_ext = (None if compact else self.alpha), r
         res.gamma = gamma[c] if gamma is not None else None
         res.gamma_lat = gamma_lat[c] if gamma_lat is not None else None
         res.dyn_marg = dyn[c] if dyn is not None else None
         res.r = r[c] if r is not None else None
         # local sums; the caller all-reduces them together with the spike-weighted statistics
-        res.tw = self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
-        res.log_marginal = self.lmr[c].sum(dtype=torch.float64)
+        # (the compact path leaves sum_t gamma to the statistics GEMM: ones column of the fp16 counts)
+        res.tw = None if compact else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
+        res.log_marginal = lmr[c].sum(dtype=torch.float64)
         res.n_relay_fwd, res.n_relay_bwd = n_relay_f, n_relay_b
         res.seam_err_fwd = float(ef.max()) if ef.numel() else 0.0
         res.seam_err_bwd = float(eb.max()) if eb.numel() else 0.0

@@ -84,10 +84,20 @@ class LazyHostArray(np.lib.mixins.NDArrayOperatorsMixin):
     copy, so derived quantities cost no device memory until someone asks for them.
     """
 
-    def __init__(self, tensor, transform=None):
-        self._t = tensor
+    def __init__(self, tensor, transform=None, shape=None, producer=None):
+        """tensor: device tensor, or None with `producer` (a callable returning the device tensor, run on
+        first use) and `shape`."""
+        self._tensor = tensor
+        self._producer = producer
+        self._shape = tuple(shape) if shape is not None else None
         self._f = transform
         self._host = None
+
+    @property
+    def _t(self):
+        if self._tensor is None:
+            self._tensor = self._producer()
+        return self._tensor
 
     def device_tensor(self):
         return self._t if self._f is None else self._f(self._t)
@@ -103,22 +113,24 @@ class LazyHostArray(np.lib.mixins.NDArrayOperatorsMixin):
 
     @property
     def shape(self):
-        return tuple(self._t.shape)
+        return self._shape if self._shape is not None else tuple(self._t.shape)
 
     @property
     def ndim(self):
-        return self._t.dim()
+        return len(self.shape)
 
     @property
     def size(self):
-        return self._t.numel()
+        return int(np.prod(self.shape))
 
     @property
     def dtype(self):
+        if self._tensor is None:
+            return np.dtype(np.float32)
         return torch.empty(0, dtype=self._t.dtype).numpy().dtype
 
     def __len__(self):
-        return self._t.shape[0]
+        return self.shape[0]
 
     def __getitem__(self, idx):
         if self._host is not None:
@@ -143,4 +155,5 @@ class LazyHostArray(np.lib.mixins.NDArrayOperatorsMixin):
         return getattr(self.numpy(), name)
 
     def __repr__(self):
-        return "LazyHostArray(shape=%s, dtype=%s, on %s)" % (self.shape, self.dtype, self._t.device)
+        where = self._tensor.device if self._tensor is not None else "device (not generated yet)"
+        return "LazyHostArray(shape=%s, dtype=%s, on %s)" % (self.shape, self.dtype, where)

@@ -108,16 +108,22 @@ def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None):
 class CountsF16:
     """fp16 copy of the spike counts for the tensor-core kernels ([T, ld16], zero padded)."""
 
-    def __init__(self, y):
+    def __init__(self, y, ones_col=False):
+        """ones_col: append a column of ones (index N) so that the statistics GEMM also returns sum_t gamma
+        (reference fit_tuning_helper.py:41) as column N of its output; the emission GEMM multiplies it by the
+        zero padding of its right-hand operand."""
         lib = _lib.load()
         _f32(y, "y", 2)
         self.T, self.N = y.shape
-        self.ld = (self.N + 7) // 8 * 8
+        self.ones_col = bool(ones_col)
+        self.ld = (self.N + (1 if ones_col else 0) + 7) // 8 * 8
         self.data = torch.empty((self.T, self.ld), dtype=torch.float16, device=y.device)
         self._inexact = torch.zeros(1, dtype=torch.int32, device=y.device)
         check(lib.pmg_counts_to_f16(self.T, self.N, _p(y), self.N, _p(self.data), self.ld, _p(self._inexact),
                                     _stream()), "pmg_counts_to_f16")
         _count(1)
+        if ones_col:
+            self.data[:, self.N] = 1.0
         self._exact = None
 
     @property
@@ -196,7 +202,7 @@ class EmissionOperands:
     The fp16 tensor-core kernel is used whenever A is exact in fp16 (integer counts <= 2048 and 0/1 masks);
     otherwise the fp32 CUDA-core tiles."""
 
-    def __init__(self, y, ma_neuron=None, dt_l=None, impl=0):
+    def __init__(self, y, ma_neuron=None, dt_l=None, impl=0, ones_col=False):
         _f32(y, "y", 2)
         self.T, self.N = y.shape
         self.mode = 0
@@ -223,7 +229,8 @@ class EmissionOperands:
             self.A = y
             self.lgam = lgamma_rowsum(y, ma_neuron)
         # per-bin dt is not fp16-exact: that path always runs on the fp32 tiles
-        self.A16 = CountsF16(self.A) if (impl == 0 and not self.per_bin_dt) else None
+        self.A16 = (CountsF16(self.A, ones_col=(ones_col and self.mode == 0))
+                    if (impl == 0 and not self.per_bin_dt) else None)
 
     @property
     def tensor_cores(self):
@@ -358,6 +365,39 @@ def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_o
     _count(1)
 
 
+def scan_compact_supported(op, likelihood_scale):
+    """True when the EM fast path (pmg_forward_compact / pmg_backward_compact) covers this transition."""
+    tr = op.cstruct()
+    return bool(_lib.load().pmg_scan_compact_supported(C.byref(tr), float(likelihood_scale)))
+
+
+def forward_compact(plan, op, ll, ax, halo_state=None, fwd_end=None, first_out=None, carry_in=None, mode=0,
+                    chain_ids=None, warm_in=None, warm_out=None):
+    """Forward pass writing the compact filtered posterior ax [T, K+4] (alpha[0,:], a1s, lmr per bin)."""
+    lib = _lib.load()
+    tr = op.cstruct()
+    n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
+    wp, ws = _warm(warm_in)
+    check(lib.pmg_forward_compact(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(carry_in), wp, ws,
+                                  _p(warm_out), _p(ax), ax.shape[1], _p(halo_state), _p(fwd_end), _p(first_out),
+                                  int(mode), _p(chain_ids), n_ids, _stream()), "pmg_forward_compact")
+    _count(1)
+
+
+def backward_compact(plan, op, ll, ax, gamma16, beta_halo=None, beta_end=None, beta_in=None,
+                     mode=0, chain_ids=None, warm_in=None, warm_out=None):
+    """Backward pass of an EM iteration: fp16 pieces of the latent posterior (and the seam messages)."""
+    lib = _lib.load()
+    tr = op.cstruct()
+    n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
+    wp, ws = _warm(warm_in)
+    check(lib.pmg_backward_compact(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(ax), ax.shape[1],
+                                   _p(beta_in), wp, ws, _p(warm_out), _p(gamma16), gamma16.shape[2],
+                                   _p(beta_halo), _p(beta_end), int(mode), _p(chain_ids), n_ids,
+                                   _stream()), "pmg_backward_compact")
+    _count(1)
+
+
 def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1e-20):
     lib = _lib.load()
     check(lib.pmg_seam_check(int(n), int(length), C.c_void_p(est_ptr), int(ld_est), C.c_void_p(truth_ptr),
@@ -417,9 +457,10 @@ def split_f16(src, out=None):
 
 
 def atb_f16(g16, y16, K, out=None):
-    """yw[K,N] = sum_t gamma[t,:K]^T y[t,:N] on the tensor cores (fp16 pieces, fp32 accumulation)."""
+    """yw[K,N] = sum_t gamma[t,:K]^T y[t,:N] on the tensor cores (fp16 pieces, fp32 accumulation).
+    With a ones column in y16 the result is [K, N+1] and its last column is sum_t gamma."""
     lib = _lib.load()
-    T, N = y16.T, y16.N
+    T, N = y16.T, y16.N + (1 if y16.ones_col else 0)
     if g16.shape[1] != T:
         raise ValueError("posterior pieces have %d bins, counts have %d" % (g16.shape[1], T))
     if out is None:
@@ -491,3 +532,29 @@ def tuning_softplus(Phi, W):
     check(lib.pmg_tuning_softplus(K, B, N, _p(Phi), _p(W), _p(out), _stream()), "pmg_tuning_softplus")
     _count(1)
     return out
+
+
+# ----------------------------------------------------------------------------- initial posterior (jax bit stream)
+def threefry_posterior_init(T, K, key, random_scale, device, t_offset=0, T_total=None, want_post=False,
+                            want_log=False, g16=None, g16_row0=0, want_tw=False):
+    """Rows [t_offset, t_offset+T) of the reference's initial posterior (core.py:571-583) generated on the
+    device with jax.random's threefry stream.  g16: optional [2, T_ext, ldg] fp16 piece buffer; rows
+    g16_row0 .. g16_row0+T-1 receive the hi/lo pieces.  Returns (post | None, logpost | None, tw fp32 | None)."""
+    from . import jaxprng
+    lib = _lib.load()
+    k = jaxprng.as_key(key)
+    T_total = int(T if T_total is None else T_total)
+    f32 = dict(dtype=torch.float32, device=device)
+    post = torch.empty((T, K), **f32) if want_post else None
+    logp = torch.empty((T, K), **f32) if want_log else None
+    tw = torch.empty(K, dtype=torch.float64, device=device) if want_tw else None
+    gptr, ldg, stride = None, 0, 0
+    if g16 is not None:
+        ldg = g16.shape[2]
+        stride = g16.shape[1] * ldg
+        gptr = C.c_void_p(g16.data_ptr() + int(g16_row0) * ldg * 2)
+    check(lib.pmg_threefry_posterior_init(int(T), int(K), int(t_offset), T_total, int(k[0]), int(k[1]),
+                                          float(random_scale), _p(post), K, _p(logp), K, gptr, ldg, stride,
+                                          _p(tw), _stream()), "pmg_threefry_posterior_init")
+    _count(1)
+    return post, logp, (tw.to(torch.float32) if tw is not None else None)

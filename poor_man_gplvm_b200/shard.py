@@ -79,6 +79,14 @@ class TimeShard:
         return self._exchange(to_left, to_right, like if to_right is not None else None,
                               like if to_left is not None else None)
 
+    def block_offset(self, T):
+        """(first global bin of this rank's block, total number of bins) for a local block of T bins."""
+        if not self.active:
+            return 0, int(T)
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(T), group=self.group)
+        return int(sum(sizes[:self.rank])), int(sum(sizes))
+
     def allreduce_sum_(self, *tensors):
         """In-place sum over ranks of several tensors packed into one collective."""
         if not self.active:

@@ -178,6 +178,75 @@ def test_chunking_is_a_numerical_noop(ops):
     assert abs(float(b.log_marginal) - lma) < 1e-6 * abs(lma)
 
 
+# ----------------------------------------------------------------------------- compact (EM fast path) kernels
+def _run_scan_compact(ops, ll, hostop, M, scale, chunk_len, halo):
+    from poor_man_gplvm_b200.estep import EStep
+    T, K = ll.shape
+    op = ops.MoveOperator(hostop, M, torch.device("cuda"))
+    es = EStep(torch.zeros((T, 1), device="cuda"), op, None, None, scale, halo=halo, chunk_len=chunk_len)
+    assert es.compact_ok
+    es.ll.copy_(dev(ll))
+    es.emission = lambda tuning: es.ll
+    g16 = ops.new_gamma16(T, K, torch.device("cuda"))
+    res = es.run(None, want_gamma_lat=False, gamma16=g16)
+    return es, res, (g16[0].float() + g16[1].float())[:, :K]
+
+
+COMPACT_CASES = [
+    # K, mv, T, chunk_len, halo -> (pairs per lane, band capacity)
+    (24, 1.0, 200, 200, 0),         # QP=4, single exact chain
+    (96, 1.0, 400, 100, 64),        # QP=4, chains + halo
+    (200, 1.0, 603, 128, 64),       # QP=4, ragged last chain, odd chunk count
+    (248, 1.0, 300, 75, 50),        # QP=7 (K + 4 > 31*8)
+    (400, 1.0, 3001, 256, 128),     # QP=7, many ring wraps, headline K
+    (432, 1.0, 260, 90, 64),        # QP=8
+    (488, 0.7, 150, 50, 40),        # QP=8, narrow kernel
+    (400, 1.6, 500, 125, 96),       # W in (5, 10]: wide-band instantiation
+    (104, 1.8, 300, 100, 64),       # wide band, small K -> QP=7
+]
+
+
+@pytest.mark.parametrize("K,mv,T,chunk_len,halo", COMPACT_CASES)
+def test_compact_scan_matches_linear_oracle(ops, K, mv, T, chunk_len, halo):
+    N = 20
+    d = make_dataset(T, N, K, seed=K + 1)
+    P, logP, M, logM, hostop = _transition(K, mv)
+    assert hostop["W"] <= 10
+    ma_l = np.ones(K); ma_l[K // 3] = 0
+    ll = lin.emission_gemm_form(d["y"], d["tuning_true"], np.ones(N), ma_l).astype(np.float32)
+    scale = 0.9
+    want = lin.e_step(d["y"], d["tuning_true"], P.astype(np.float64), M.astype(np.float64), np.ones(N), ma_l,
+                      likelihood_scale=scale)
+    es, res, glat = _run_scan_compact(ops, ll, hostop, M, scale, chunk_len, halo)
+    assert res.alpha is None                                  # the compact path was taken
+    assert np.max(np.abs(host(glat) - want["gamma"].sum(axis=1))) < 1e-5
+    assert abs(float(res.log_marginal) - want["log_marginal"]) < 1e-4 * abs(want["log_marginal"])
+    assert np.max(np.abs(host(res.lmr) - want["lmr"])) < 1e-3
+    assert res.tw is None                                     # left to the statistics GEMM (ones column)
+    # compact filtered posterior: alpha[0,:] stored, alpha[1,:] = a1s * E
+    ax = host(es.ax)
+    assert np.max(np.abs(ax[:, :K] - want["alpha"][:, 0])) < 1e-5
+    E = np.exp2((ll - ll.max(axis=1, keepdims=True)) * np.float32(scale * 1.4426950408889634))
+    assert np.max(np.abs(ax[:, K:K + 1] * E - want["alpha"][:, 1])) < 1e-5
+
+
+def test_compact_scan_equals_general_path_and_relays(ops):
+    """Same inputs through both kernel families; a useless halo forces relays on the compact path too."""
+    K, T, N = 200, 1500, 25
+    d = make_dataset(T, N, K, seed=21)
+    P, logP, M, logM, hostop = _transition(K, 1.0)
+    ll = lin.emission_gemm_form(d["y"], d["tuning_true"], np.ones(N), np.ones(K)).astype(np.float32)
+    _, full = _run_scan(ops, ll, hostop, M, 1.0, chunk_len=250, halo=128, want_r=False)
+    gl_full, lm_full = host(full.gamma_lat).copy(), float(full.log_marginal)
+    _, res, glat = _run_scan_compact(ops, ll, hostop, M, 1.0, chunk_len=250, halo=128)
+    assert np.max(np.abs(host(glat) - gl_full)) < 3e-6
+    assert abs(float(res.log_marginal) - lm_full) < 1e-6 * abs(lm_full)
+    _, res2, glat2 = _run_scan_compact(ops, ll, hostop, M, 1.0, chunk_len=100, halo=2)
+    assert res2.n_relay_fwd >= 1 and res2.n_relay_bwd >= 1
+    assert np.max(np.abs(host(glat2) - gl_full)) < 1e-5
+    assert abs(float(res2.log_marginal) - lm_full) < 1e-5 * abs(lm_full)
+
+
 # ----------------------------------------------------------------------------- time-reduction GEMM
 @pytest.mark.parametrize("T,M,N", [(1, 3, 5), (1000, 100, 30), (4097, 130, 70), (20000, 400, 500)])
 @pytest.mark.parametrize("impl", [0, 1])

@@ -147,3 +147,40 @@ def test_hyperparam_override_save_every_and_pickle():
     assert np.max(np.abs(np.exp(got["log_posterior_all_saved"][1]) - np.exp(want["log_posterior_all_saved"][1]))) < 5e-5
     m2 = pickle.loads(pickle.dumps(model))
     assert np.array_equal(m2.tuning, model.tuning) and m2.adam_runner is None
+
+
+def test_device_posterior_init_matches_host_threefry():
+    """pmg_threefry_posterior_init == jaxprng (jax.random's bit stream) incl. odd sizes, row offsets, pieces."""
+    from poor_man_gplvm_b200 import jaxprng as jr, ops
+    dev = torch.device("cuda")
+    for T, K, key in [(7, 5, 0), (33, 100, 123), (64, 401, 9)]:
+        u = jr.uniform(jr.PRNGKey(key), (T, K)) * np.float32(0.1)
+        want = u / u.sum(axis=1, keepdims=True)
+        post, logp, tw = ops.threefry_posterior_init(T, K, key, 0.1, dev, want_post=True, want_log=True, want_tw=True)
+        assert np.allclose(post.cpu().numpy(), want, rtol=3e-7, atol=0)
+        assert np.allclose(np.exp(logp.cpu().numpy()), want, rtol=2e-6)
+        assert np.allclose(tw.cpu().numpy(), want.sum(axis=0), rtol=1e-6)
+        # rows 10..19 of the same global draw, written as fp16 pieces into rows 3.. of a larger buffer
+        if T > 20:
+            g16 = ops.new_gamma16(16, K, dev)
+            ops.threefry_posterior_init(10, K, key, 0.1, dev, t_offset=10, T_total=T, g16=g16, g16_row0=3)
+            rec = (g16[0].float() + g16[1].float()).cpu().numpy()[:, :K]
+            assert np.allclose(rec[3:13], want[10:20], rtol=0, atol=1e-7)
+            assert np.all(rec[:3] == 0) and np.all(rec[13:] == 0)
+
+
+def test_fit_em_default_key_draws_reference_posterior_on_device():
+    """fit_em(y) without log_posterior_init: the posterior is drawn on the device from `key` with jax's stream;
+    the result equals a run that is handed the same array explicitly, and em_res exposes it lazily."""
+    import poor_man_gplvm_b200 as pmg
+    N, K, T = 20, 64, 700
+    d = make_dataset(T, N, K, seed=4)
+    m1 = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=8.0)
+    m2 = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=8.0)
+    assert np.array_equal(m1.params, m2.params)                 # initialize_params is deterministic in rng_init_int
+    r1 = m1.fit_em(d["y"], key=11, n_iter=3, m_step_maxiter=30, m_step_tol=-1)
+    lp0, _ = m2.init_latent_posterior(T, 11)
+    r2 = m2.fit_em(d["y"], n_iter=3, log_posterior_init=lp0, m_step_maxiter=30, m_step_tol=-1)
+    assert np.allclose(np.asarray(r1["log_posterior_init"]), lp0, rtol=0, atol=2e-6)
+    assert np.allclose(r1["log_marginal_l"], r2["log_marginal_l"], rtol=2e-6)
+    assert np.max(np.abs(r1["posterior_latent_marg"] - r2["posterior_latent_marg"])) < 2e-5

@@ -79,9 +79,11 @@ def test_move_operator_factorisation_reconstructs_P0(K, mv):
 
 def test_plan_chunks_bounds():
     from poor_man_gplvm_b200.estep import plan_chunks
-    assert plan_chunks(1000, 256, 148) == 1000                    # short sequences: one exact chain
+    from poor_man_gplvm_b200.estep import MIN_CHUNK_OVER_HALO
+    assert plan_chunks(700, 256, 148) == 700                      # short sequences: one exact chain
     c = plan_chunks(10 ** 6, 256, 148)
-    assert c >= 4 * 256 and (10 ** 6 + c - 1) // c <= 148 * 8
+    assert c >= MIN_CHUNK_OVER_HALO * 256 and (10 ** 6 + c - 1) // c <= 148 * 8
+    assert (10 ** 6 + c - 1) // c > 148 * 7                       # the headline run fills every SM
     assert plan_chunks(5000, 0, 148) == 5000
 
 
@@ -118,3 +120,31 @@ def test_lazy_host_array_behaves_like_numpy():
     assert np.allclose(a - want, 0, atol=1e-5) and np.allclose(want - a, 0, atol=1e-5) and np.allclose(np.log(a), np.log(want))
     assert np.isclose(a.sum(), want.sum(), rtol=1e-5) and a.argmax() == want.argmax()
     assert np.array_equal(to_numpy(t), t.numpy())
+
+
+# ----------------------------------------------------------------------------- jax.random bit streams
+def test_threefry_known_answers():
+    """Random123 threefry2x32-20 known-answer vectors (also jax's own tests/random_test.py::testThreefry2x32)."""
+    from poor_man_gplvm_b200 import jaxprng as jr
+    def enc(k, c):
+        a, b = jr.threefry2x32(k[0], k[1], np.uint32(c[0]), np.uint32(c[1]))
+        return int(a), int(b)
+    assert enc((0, 0), (0, 0)) == (0x6b200159, 0x99ba4efe)
+    assert enc((0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff)) == (0x1cb996fc, 0xbb002be7)
+    assert enc((0x13198a2e, 0x03707344), (0x243f6a88, 0x85a308d3)) == (0xc4923a9c, 0x483df7a0)
+
+
+def test_jax_random_documented_values():
+    """Values printed in the JAX documentation for PRNGKey(0) (recalled, JAX is not installable here):
+    random.split(key) and the quickstart's random.normal(key, (10,))."""
+    from poor_man_gplvm_b200 import jaxprng as jr
+    key = jr.PRNGKey(0)
+    assert jr.split(key).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    want = np.array([-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442, -0.67135346,
+                     -0.5908641, 0.73168886, 0.5673026], dtype=np.float32)
+    assert np.allclose(jr.normal(key, (10,)), want, rtol=0, atol=2e-7)
+    u = jr.uniform(jr.PRNGKey(7), (5, 3))
+    assert u.shape == (5, 3) and u.dtype == np.float32 and np.all((u >= 0) & (u < 1))
+    # odd sizes use the padded counter layout
+    assert np.array_equal(jr.random_bits(key, 5)[:2], jr.random_bits(key, 5)[:2])
+    assert jr.random_bits(key, 5).shape == (5,)
