@@ -49,7 +49,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -59,12 +59,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Samples whose nvidia-smi timestamp falls inside [t_begin, t_end] (time.time() values) -- the sampler
+        is started well before the timed region because nvidia-smi needs ~0.2 s to produce its first line."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -73,21 +75,30 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, n_all = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
+            n_all += 1
+            if t_begin is not None:
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    continue
+                if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                    continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_outside_timed_region": n_all - len(sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,16 +245,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        loop.iteration()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        loop.iteration()
+    barrier()
     launches0 = ops.LAUNCHES
     timer.enabled = True
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall_begin = time.time()
     ev0.record()
     relays = 0
     n_adam = []
@@ -254,8 +266,9 @@ def run_ours(args):
         n_adam.append(m_res[2])
     ev1.record()
     barrier()
+    wall_end = time.time()
     timer.enabled = False
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall_begin, wall_end) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = ops.LAUNCHES - launches0
     if world > 1:
@@ -324,6 +337,28 @@ def run_ours(args):
                        "materialises on the host, core.py:688-690); bytes are per EM iteration"}
         del em, y_host
 
+    # ---- decode throughput (second half of BASELINE.json's metric): device-resident spikes, fitted tuning
+    decode = None
+    if not args.no_decode and world == 1:
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        tun = res_tuning = m_res[4]
+        ms_nb = timed(lambda: model.decode_latent_naive_bayes(y_dev, tuning=tun, return_device=True))
+        ms_dec = timed(lambda: model.decode_latent(y_dev, tuning=tun, return_device=True), reps=2)
+        decode = {"unit": "bins/s", "naive_bayes": T / (ms_nb * 1e-3), "naive_bayes_ms": ms_nb,
+                  "decode_latent": T / (ms_dec * 1e-3), "decode_latent_ms": ms_dec,
+                  "note": "decode_latent_naive_bayes / decode_latent (smoother + transition counts) on the bench "
+                          "workload, spikes and results resident on the device"}
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         rate, parts = cpu_reference_rate(N, K, ls, mv, args.cpu_sample_bins, 1, 0, T)
@@ -349,7 +384,8 @@ def run_ours(args):
                            "n_chain": loop.es.plan.n_chain, "chunk_len": loop.es.chunk_len, "halo": loop.es.halo,
                            "seam_relays_in_timed_region": relays, "adam_steps_per_iter": n_adam},
                 "phases_ms_per_step": per, "roofline": roofline, "roofline_all": roof_all,
-                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "decode": decode, "gpu_launches": launches,
+                "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -358,7 +394,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
@@ -369,6 +405,7 @@ def main():
     ap.add_argument("--cpu-sample-bins", type=int, default=200)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

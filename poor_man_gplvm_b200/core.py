@@ -112,7 +112,8 @@ class EMLoop:
         if self.W.shape != (self.Phi.shape[1], model.n_neuron):
             raise ValueError("params shape %s does not match basis %s" % (tuple(self.W.shape), tuple(self.Phi.shape)))
         self.state = ops.AdamState(self.W)
-        self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len, shard=shard)
+        self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len, shard=shard,
+                        em_mode=True)
         self.shard = self.es.shard
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
@@ -233,12 +234,14 @@ class PoissonGPLVMJump1D:
     def _dev(self, a, dtype=torch.float32):
         if isinstance(a, torch.Tensor):
             return a.to(device=self.device, dtype=dtype).contiguous()
-        return torch.as_tensor(np.ascontiguousarray(np.asarray(a)), device=self.device).to(dtype).contiguous()
+        if isinstance(a, hostio.LazyHostArray):
+            return a.device_tensor().to(device=self.device, dtype=dtype).contiguous()
+        return hostio.to_device(np.asarray(a), self.device).to(dtype).contiguous()
 
     @staticmethod
-    def _host(t):
+    def _host(t, out=None):
         """device tensor -> NumPy (pinned, pipelined copy for the T-sized arrays)"""
-        return hostio.to_numpy(t) if isinstance(t, torch.Tensor) else np.asarray(t)
+        return hostio.to_numpy(t, out=out) if isinstance(t, torch.Tensor) else np.asarray(t)
 
     # ------------------------------------------------------------------ reference API
     def get_tuning(self, params, hyperparam, tuning_basis):
@@ -442,9 +445,15 @@ class PoissonGPLVMJump1D:
         self.p_jump_to_move = hyperparam_.get('p_jump_to_move', self.p_jump_to_move)
 
         tm = _Timing()
+        T, K = int(np.shape(y_in)[0]), self.n_latent_bin
         y_dev = self._dev(y_in)                       # the one host->device copy of the spikes
         tm.mark("h2d_y")
-        T, K = y_dev.shape[0], self.n_latent_bin
+        # the host copies of the T-sized results are allocated now and their pages faulted in by background
+        # threads while the EM iterations run on the GPU
+        bufs = None
+        if not return_device and n_iter > 0 and T * K >= (1 << 22):
+            bufs = hostio.HostBuffers([("posterior", (T, 2, K), np.float32), ("latent", (T, K), np.float32),
+                                       ("dynamics", (T, 2), np.float32)])
         if save_every is None:
             save_every = n_iter
         P, logP, M, logM, op = self._transition_pack(hyperparam_)
@@ -526,11 +535,15 @@ class PoissonGPLVMJump1D:
                        'log_marginal_l': [v for v in lml_host],
                        'm_step_res_l': m_step_res_l})
         if n_iter > 0:
+            take = (lambda n: bufs.take(n)) if bufs is not None else (lambda n: None)
+            conv_to = (lambda t, n: t) if return_device else (lambda t, n: self._host(t, out=take(n)))
             em_res.update({'log_posterior_final': lazy_log(res.gamma),
                            'log_marginal': lml_host[-1],
-                           'posterior': conv(res.gamma),
-                           'posterior_latent_marg': _rewrap_tsd(conv(res.gamma_lat), t_l),
-                           'posterior_dynamics_marg': _rewrap_tsd(conv(res.dyn_marg), t_l)})
+                           'posterior': conv_to(res.gamma, "posterior"),
+                           'posterior_latent_marg': _rewrap_tsd(conv_to(res.gamma_lat, "latent"), t_l),
+                           'posterior_dynamics_marg': _rewrap_tsd(conv_to(res.dyn_marg, "dynamics"), t_l)})
+        if bufs is not None:
+            bufs.close()
         tm.mark("outputs")
         tm.report()
         return em_res

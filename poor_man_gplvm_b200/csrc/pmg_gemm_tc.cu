@@ -83,7 +83,7 @@ __global__ void emission_prepare_f16_kernel(int K, int N, const float* __restric
 // ---------------------------------------------------------------------------------------------
 struct EmissionTcParams {
   int64_t T;
-  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages;
+  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages, stagger, nostore, brep, brep_rows;
   uint32_t idesc, tmem_cols;
   const float* lam_sum;
   const float* lgam;
@@ -93,9 +93,155 @@ struct EmissionTcParams {
 };
 
 constexpr int EM_PB = 2;   // fp16 pieces of loglam
+constexpr int EM_MI = 2;   // 128-row tiles per work unit: both share every right-hand tile fetched from L2
 
+// Work unit = 256 time bins x BN latent bins: two TMEM accumulators side by side, one pass over the neurons.
+// The kernel is bound by the L2 -> shared-memory feed of the (small, shared) right-hand operand, so a unit
+// uses each right-hand tile for two row tiles; the epilogue of accumulator 0 overlaps the first MMAs of the
+// next unit (per-accumulator "drained" barriers), the TMA producer keeps prefetching throughout.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const EmissionTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;
+  const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
+  const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + EM_MI);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    for (int b = 0; b < EM_MI; ++b) mbar_init(&tempty[b], 128);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_mpairs = (p.n_mtiles + EM_MI - 1) / EM_MI;
+  const int n_units = n_mpairs * p.n_ntiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      // every CTA walks the K blocks in a different rotation, so that at any moment the CTAs read different
+      // lines of the right-hand operand instead of all hitting the same L2 slices
+      const int kb0 = p.stagger ? (int)(blockIdx.x % p.n_kblocks) : 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int mp = unit / p.n_ntiles, nt = unit % p.n_ntiles;
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          int kbe = kb + kb0;
+          if (kbe >= p.n_kblocks) kbe -= p.n_kblocks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);
+#pragma unroll
+          for (int mi = 0; mi < EM_MI; ++mi)      // rows past T are zero-filled by the TMA unit
+            tma_load_2d(sA + mi * TC_A_BYTES, &tmA, &full[stage], kbe * TC_BK, (mp * EM_MI + mi) * TC_BM);
+#pragma unroll
+          for (int pc = 0; pc < EM_PB; ++pc)
+            tma_load_2d(sA + EM_MI * TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kbe * TC_BK,
+                        p.brep_rows * (int)(blockIdx.x % p.brep) + pc * p.Kpad + nt * BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+        const uint32_t drained = (uint32_t)(it & 1) ^ 1;      // parity of "the previous unit's epilogue is done"
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+          for (int mi = 0; mi < EM_MI; ++mi) {
+            if (kb == 0) {
+              mbar_wait(&tempty[mi], drained);
+              tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)(mi * BN);
+#pragma unroll
+            for (int pc = 0; pc < EM_PB; ++pc) {
+              const uint32_t sB = sA + EM_MI * TC_A_BYTES + pc * b_bytes;
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t ad = make_smem_desc(sA + mi * TC_A_BYTES + k * 32, 16, 1024);
+                const uint64_t bd = make_smem_desc(sB + k * 32, 16, 1024);
+                mma_f16_ss(d_tmem, ad, bd, p.idesc, (kb | pc | k) != 0);
+              }
+            }
+          }
+          mma_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tfull);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    int it = 0;
+    const bool vec_ok = (p.ldll & 3) == 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const int mp = unit / p.n_ntiles, nt = unit % p.n_ntiles;
+      mbar_wait(tfull, (uint32_t)(it & 1));
+      tc_fence_after();
+      for (int mi = 0; mi < EM_MI; ++mi) {
+        const int64_t t = (int64_t)(mp * EM_MI + mi) * TC_BM + q * 32 + lane;
+        const bool t_ok = t < p.T;
+        const float lg = t_ok ? p.lgam[t] : 0.f;
+        float* orow = p.ll + (size_t)(t_ok ? t : 0) * p.ldll;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mi * BN);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(taddr + c0, r);
+          tmem_ld_wait();
+          const int k0 = nt * BN + c0;
+          if (t_ok && k0 < p.K && !p.nostore) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int k = k0 + j;
+              float x = __uint_as_float(r[j]);
+              if (k < p.K) {
+                x = x - __ldg(p.lam_sum + k) - lg;
+                if (p.ma_latent && __ldg(p.ma_latent + k) == 0.f) x = kVeryNegLL;
+              }
+              v[j] = x;
+            }
+            if (vec_ok && k0 + 16 <= p.K) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(orow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (k0 + j < p.K) orow[k0 + j] = v[j];
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[mi]);                // accumulator mi may be overwritten by the next unit
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// previous structure (one 128-row tile per unit, double-buffered accumulator), kept selectable for experiments
+__global__ void __launch_bounds__(TC_THREADS, 1)
+emission_tc_kernel_v1(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const EmissionTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -127,14 +273,18 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_ntiles, nt = tile % p.n_ntiles;
+        const int kb0 = p.stagger ? (int)(blockIdx.x % p.n_kblocks) : 0;
         for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          int kbe = kb + kb0;
+          if (kbe >= p.n_kblocks) kbe -= p.n_kblocks;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
-          tma_load_2d(sA, &tmA, &full[stage], kb * TC_BK, mt * TC_BM);
+          tma_load_2d(sA, &tmA, &full[stage], kbe * TC_BK, mt * TC_BM);
 #pragma unroll
           for (int pc = 0; pc < EM_PB; ++pc)
-            tma_load_2d(sA + TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kb * TC_BK, pc * p.Kpad + nt * BN);
+            tma_load_2d(sA + TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kbe * TC_BK,
+                        p.brep_rows * (int)(blockIdx.x % p.brep) + pc * p.Kpad + nt * BN);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -275,7 +425,10 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   CUtensorMap tmA, tmB;
   int rc = make_tmap_f16(&tmA, y16, (uint64_t)T, (uint64_t)ld16, (uint64_t)ld16, TC_BM);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
-  rc = make_tmap_f16(&tmB, loglam16, (uint64_t)EM_PB * Kpad, (uint64_t)ld16, (uint64_t)ld16, (uint32_t)BN);
+  // experiment knob PMG_EM_BREP=r: the caller provides r identical copies of the right-hand operand back to back
+  static const int brep_avail = std::getenv("PMG_EM_BREP") ? std::atoi(std::getenv("PMG_EM_BREP")) : 1;
+  rc = make_tmap_f16(&tmB, loglam16, (uint64_t)EM_PB * Kpad * (brep_avail > 0 ? brep_avail : 1), (uint64_t)ld16,
+                     (uint64_t)ld16, (uint32_t)BN);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
 
   EmissionTcParams p;
@@ -283,7 +436,13 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   p.n_kblocks = (int)((ld16 + TC_BK - 1) / TC_BK);
   p.n_mtiles = (int)((T + TC_BM - 1) / TC_BM);
   p.n_ntiles = n_ntiles;
-  const uint32_t stage_bytes = TC_A_BYTES + EM_PB * BN * TC_BK * 2;
+  static const int kver = std::getenv("PMG_EM_KERNEL") ? std::atoi(std::getenv("PMG_EM_KERNEL")) : 1;
+  static const int nostore = std::getenv("PMG_EM_NOSTORE") ? std::atoi(std::getenv("PMG_EM_NOSTORE")) : 0;
+  static const int brep = std::getenv("PMG_EM_BREP") ? std::atoi(std::getenv("PMG_EM_BREP")) : 1;
+  p.nostore = nostore;
+  p.brep = brep_avail > 0 && brep <= brep_avail ? brep : 1;
+  p.brep_rows = EM_PB * Kpad;
+  const uint32_t stage_bytes = (kver == 2 ? EM_MI : 1) * TC_A_BYTES + EM_PB * BN * TC_BK * 2;
   // 227 KB of shared memory per CTA minus alignment slack and barriers
   int stages = (int)((225 * 1024) / stage_bytes);
   // measured on B200 at the headline shape: 2 stages 1.95 ms, 3 stages 2.08 ms (the loads of all CTAs hit the
@@ -293,6 +452,8 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   if (stages > 8) stages = 8;
   if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
   p.stages = stages;
+  static const int stagger_env = std::getenv("PMG_EM_STAGGER") ? std::atoi(std::getenv("PMG_EM_STAGGER")) : 1;
+  p.stagger = stagger_env;
   p.idesc = make_idesc_f16(TC_BM, BN, 0, 0, 0);
   p.tmem_cols = pow2_cols(2 * BN);
   p.lam_sum = lam_sum; p.lgam = lgam; p.ma_latent = ma_latent; p.ll = ll; p.ldll = ldll;
@@ -302,8 +463,15 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   int dev = 0, sms = 0;
   PMG_CUDA_CHECK(cudaGetDevice(&dev));
   PMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int n_tiles = p.n_mtiles * p.n_ntiles;
-  const int grid = n_tiles < sms ? n_tiles : sms;
+  if (kver != 2) {
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = p.n_mtiles * p.n_ntiles;
+    emission_tc_kernel_v1<<<n_tiles < sms ? n_tiles : sms, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    PMG_LAUNCH_CHECK();
+    return PMG_OK;
+  }
+  const int n_units = ((p.n_mtiles + EM_MI - 1) / EM_MI) * p.n_ntiles;
+  const int grid = n_units < sms ? n_units : sms;
   emission_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
@@ -326,18 +494,23 @@ struct AtbTcParams {
   float* partial;    // [splits][K][N]
 };
 
+// One CTA owns TWO 128-neuron row tiles (two TMEM accumulators side by side) for one tile of latent bins and
+// one time split, so that every posterior tile fetched from L2 feeds 256 output rows: the kernel is bound by
+// the L2 -> shared-memory feed, not by the tensor pipe.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG,
               const AtbTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int mt = blockIdx.x, nt = blockIdx.y, sp = blockIdx.z;
+  const int mp = blockIdx.x, nt = blockIdx.y, sp = blockIdx.z;
+  const int n_mi = (2 * mp + 1 < p.n_mtiles) ? 2 : 1;          // row tiles of this CTA
   const int k_base = nt * p.BN;
   int bn = p.K - k_base;                         // columns of this tile, rounded up to the 64-wide atoms
   bn = (bn + 63) / 64 * 64;
   if (bn > p.BN) bn = p.BN;
   const int n_boxes_b = bn / 64;
-  const uint32_t a_bytes = 2 * AT_BOX_BYTES;
+  const uint32_t a_tile_bytes = 2 * AT_BOX_BYTES;              // 128 neurons x 32 time bins
+  const uint32_t a_bytes = 2 * a_tile_bytes;
   const uint32_t b_piece_bytes = (uint32_t)(p.BN / 64) * AT_BOX_BYTES;
   const uint32_t stage_bytes = a_bytes + AT_PG * b_piece_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -362,7 +535,7 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   int64_t t_end = t_begin + p.t_per_split;
   if (t_end > p.T) t_end = p.T;
   const int n_tb = t_end > t_begin ? (int)((t_end - t_begin + AT_BKT - 1) / AT_BKT) : 0;
-  const uint32_t tx_bytes = a_bytes + AT_PG * (uint32_t)n_boxes_b * AT_BOX_BYTES;
+  const uint32_t tx_bytes = (uint32_t)n_mi * a_tile_bytes + AT_PG * (uint32_t)n_boxes_b * AT_BOX_BYTES;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -372,8 +545,11 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         uint8_t* sA = smem + (size_t)stage * stage_bytes;
         const int t0 = (int)(t_begin + (int64_t)tb * AT_BKT);
         mbar_arrive_expect_tx(&full[stage], tx_bytes);
-        tma_load_2d(sA, &tmY, &full[stage], mt * TC_BM, t0);
-        tma_load_2d(sA + AT_BOX_BYTES, &tmY, &full[stage], mt * TC_BM + 64, t0);
+        for (int mi = 0; mi < n_mi; ++mi) {
+          const int m0 = (2 * mp + mi) * TC_BM;
+          tma_load_2d(sA + mi * a_tile_bytes, &tmY, &full[stage], m0, t0);
+          tma_load_2d(sA + mi * a_tile_bytes + AT_BOX_BYTES, &tmY, &full[stage], m0 + 64, t0);
+        }
         for (int pc = 0; pc < AT_PG; ++pc)
           for (int b = 0; b < n_boxes_b; ++b)
             tma_load_2d(sA + a_bytes + pc * b_piece_bytes + b * AT_BOX_BYTES, &tmG, &full[stage], k_base + b * 64,
@@ -389,15 +565,17 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+        for (int mi = 0; mi < n_mi; ++mi) {
 #pragma unroll
-        for (int pc = 0; pc < AT_PG; ++pc) {
-          const uint32_t sB = sA + a_bytes + pc * b_piece_bytes;
+          for (int pc = 0; pc < AT_PG; ++pc) {
+            const uint32_t sB = sA + a_bytes + pc * b_piece_bytes;
 #pragma unroll
-          for (int k = 0; k < AT_BKT / 16; ++k) {
-            // MN-major: atoms along M/N are one TMA box apart (LBO), 8-row atoms along time 1024 B apart (SBO)
-            const uint64_t ad = make_smem_desc(sA + k * 2048, AT_BOX_BYTES, 1024);
-            const uint64_t bd = make_smem_desc(sB + k * 2048, AT_BOX_BYTES, 1024);
-            mma_f16_ss(tmem_base, ad, bd, idesc, (tb | pc | k) != 0);
+            for (int k = 0; k < AT_BKT / 16; ++k) {
+              // MN-major: atoms along M/N are one TMA box apart (LBO), 8-row atoms along time 1024 B apart (SBO)
+              const uint64_t ad = make_smem_desc(sA + mi * a_tile_bytes + k * 2048, AT_BOX_BYTES, 1024);
+              const uint64_t bd = make_smem_desc(sB + k * 2048, AT_BOX_BYTES, 1024);
+              mma_f16_ss(tmem_base + (uint32_t)(mi * p.BN), ad, bd, idesc, (tb | pc | k) != 0);
+            }
           }
         }
         mma_commit(&empty[stage]);
@@ -407,27 +585,29 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int n = mt * TC_BM + q * 32 + lane;
     float* out = p.partial + (size_t)sp * p.K * p.N;
     if (n_tb > 0) {
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < bn; c0 += 16) {
-      uint32_t r[16];
-      if (n_tb > 0) {
-        tmem_ld_x16(taddr + c0, r);
-        tmem_ld_wait();
-      } else {
+    for (int mi = 0; mi < n_mi; ++mi) {
+      const int n = (2 * mp + mi) * TC_BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mi * p.BN);
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        uint32_t r[16];
+        if (n_tb > 0) {
+          tmem_ld_x16(taddr + c0, r);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0u;
-      }
-      if (n < p.N) {
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        if (n < p.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = k_base + c0 + j;
-          if (k < p.K) out[(size_t)k * p.N + n] = __uint_as_float(r[j]);   // lanes = consecutive neurons: coalesced
+          for (int j = 0; j < 16; ++j) {
+            const int k = k_base + c0 + j;
+            if (k < p.K) out[(size_t)k * p.N + n] = __uint_as_float(r[j]);   // lanes = consecutive neurons: coalesced
+          }
         }
       }
     }
@@ -465,8 +645,9 @@ static void atb_tc_plan(int64_t T, int K, int N, int& BN, int& n_mtiles, int& n_
   BN = K >= 256 ? 256 : (K + 63) / 64 * 64;
   n_ntiles = (K + BN - 1) / BN;
   n_mtiles = (N + TC_BM - 1) / TC_BM;
-  const int tiles = n_mtiles * n_ntiles;
-  splits = (148 + tiles - 1) / tiles;
+  const int tiles = ((n_mtiles + 1) / 2) * n_ntiles;   // a CTA owns a pair of row tiles
+  splits = 148 / tiles;
+  if (splits < 1) splits = 1;
   const int64_t max_splits = (T + 4 * AT_BKT - 1) / (4 * AT_BKT);
   if (splits > max_splits) splits = (int)max_splits;
   if (splits < 1) splits = 1;
@@ -502,12 +683,12 @@ extern "C" int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg
   atb_tc_plan(T, K, N, p.BN, p.n_mtiles, p.n_ntiles, p.splits, p.t_per_split);
   if (!workspace || workspace_bytes < (int64_t)p.splits * K * N * (int64_t)sizeof(float)) return PMG_ERR_WORKSPACE;
   p.T = T; p.K = K; p.N = N; p.partial = (float*)workspace;
-  const uint32_t stage_bytes = 2 * AT_BOX_BYTES + AT_PG * (p.BN / 64) * AT_BOX_BYTES;
+  const uint32_t stage_bytes = 4 * AT_BOX_BYTES + AT_PG * (p.BN / 64) * AT_BOX_BYTES;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
   p.stages = stages;
-  p.tmem_cols = pow2_cols(p.BN);
+  p.tmem_cols = pow2_cols(2 * p.BN);
 
   CUtensorMap tmY, tmG;
   // inner (contiguous) dimension = neurons / latent bins, outer = time; box = 32 time rows x 64 columns
@@ -518,7 +699,7 @@ extern "C" int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   cudaStream_t st = (cudaStream_t)stream;
   PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.n_mtiles, p.n_ntiles, p.splits);
+  dim3 grid((p.n_mtiles + 1) / 2, p.n_ntiles, p.splits);
   atb_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmY, tmG, p);
   PMG_LAUNCH_CHECK();
   const int64_t MN = (int64_t)K * N;

@@ -60,6 +60,15 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 ex2_2(float2 a) { return pk(ex2_ftz(a.x), ex2_ftz(a.y)); }
 
+// one lane of the (converged) warp, the same one every time: code under `if (elect_one())` is known to the
+// compiler to run in a single thread, so bulk-copy instructions are issued straight from uniform registers
+// (under `if (lane == 0)` every such instruction is wrapped in an elect/branch loop over the active lanes)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // warp-wide float max in one instruction (redux.sync.max.f32, sm_100a)
 __device__ __forceinline__ float warp_max_redux(float v) {
   float r;
@@ -117,7 +126,7 @@ struct CGeo {
 
 // writes the normalised message (v0*s0, v1*s1) as a [2,K] vector
 template <int QP>
-__device__ __noinline__ void store_msg(float* o, const float2 (&v0)[QP], float s0, const float2 (&v1)[QP], float s1,
+__device__ __forceinline__ void store_msg(float* o, const float2 (&v0)[QP], float s0, const float2 (&v1)[QP], float s1,
                                        int x0, int K) {
 #pragma unroll
   for (int p = 0; p < QP; ++p) {
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   // ---- fill the input ring
   const uint32_t row_bytes = (uint32_t)K * 4;
   const float* ll_next = c.ll + (size_t)t0 * c.ldll;             // row the next refill loads
-  if (lane == 0) {
+  if (elect_one()) {
     for (int j = 0; j < R && j < n_steps; ++j) {
       tc::mbar_arrive_expect_tx(&bars[j], row_bytes);
       bulk_load(ring + (size_t)j * KP, ll_next + (size_t)j * c.ldll, row_bytes, &bars[j]);
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   float* ax_group = ax_row;                                      // first row of the group being staged
   for (int i = 0; i < n_steps; ++i) {
     if (orow == 0 && i >= i_begin) {             // a new staging group starts: its buffer must have been read out
-      if (lane == 0) bulk_wait_read<1>();
+      if (elect_one()) bulk_wait_read<1>();
       __syncwarp();
     }
     tc::mbar_wait(&bars[slot], ring_phase);
@@ -284,9 +293,11 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
     band_pk<QP, WT>(a, pr0, tp, lane_left, lane_right);
     // every lane holds its part of ring[slot] in registers: refill the slot R steps ahead
     __syncwarp();
-    if (lane == 0 && i + R < n_steps) {
-      tc::mbar_arrive_expect_tx(&bars[slot], row_bytes);
-      bulk_load(ring + (size_t)slot * KP, ll_next, row_bytes, &bars[slot]);
+    if (i + R < n_steps) {
+      if (elect_one()) {
+        tc::mbar_arrive_expect_tx(&bars[slot], row_bytes);
+        bulk_load(ring + (size_t)slot * KP, ll_next, row_bytes, &bars[slot]);
+      }
     }
     ll_next += c.ldll;
     if (++slot == R) { slot = 0; ring_phase ^= 1; }
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
       if (orow == NB || i == n_steps - 1) {
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           for (int r = 0; r < orow; ++r)
             bulk_store(ax_group + (size_t)r * p.ldax, outb + (size_t)(og * NB + r) * KP, row_bytes);
           bulk_commit();
@@ -345,7 +356,8 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
     for (int q = 0; q < QP; ++q) u[q] = fma2(c1, Lc[q], v0[q]);
     inv_prev = inv;
   }
-  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+  if (elect_one()) bulk_wait_read<0>();
 }
 
 // ============================================================================
@@ -470,7 +482,9 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
     }
   };
   for (int j = 0; j < R; ++j) {
-    if (lane == 0 && j < n_steps) issue(j, j);
+    if (j < n_steps) {
+      if (elect_one()) issue(j, j);
+    }
     ll_next -= c.ldll;
     ax_next -= p.ldax;
   }
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
   for (int i = 0; i < n_steps; ++i) {
     const bool core = i >= i_core;
     if (core && r_out == n_rows - 1) {           // a new staging group starts
-      if (lane == 0) bulk_wait_read<1>();
+      if (elect_one()) bulk_wait_read<1>();
       __syncwarp();
     }
     tc::mbar_wait(&bars[slot], ring_phase);
@@ -544,7 +558,9 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
     }
     // all lanes are done with ring[slot]: refill it R steps ahead
     __syncwarp();
-    if (lane == 0 && i + R < n_steps) issue(slot, i + R);
+    if (i + R < n_steps) {
+      if (elect_one()) issue(slot, i + R);
+    }
     ll_next -= c.ldll;
     ax_next -= p.ldax;
     if (++slot == R) { slot = 0; ring_phase ^= 1; }
@@ -569,7 +585,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
       if (r_out == 0) {
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           for (int rr = 0; rr < n_rows; ++rr) {
             const __half* srow = outh + (size_t)(og * NB + rr) * 2 * KP;
             bulk_store(g_row + (size_t)rr * p.ldg, srow, (uint32_t)K * 2);
@@ -596,7 +612,8 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
     RLu = S2;
     inv_prev = inv;
   }
-  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+  if (elect_one()) bulk_wait_read<0>();
 }
 
 // ---- host side ---------------------------------------------------------------------------
@@ -611,9 +628,9 @@ static int compact_ring_depth(int nw, int nb) {
   return 0;
 }
 
-template <int QP, int WT>
+template <int QP, int WT, int NW>
 static int launch_fwd_c(const FwdCParams& p, int n_groups, cudaStream_t st) {
-  constexpr int NW = 8, NB = 4;
+  constexpr int NB = NW > 8 ? 2 : 4;
   const int R = compact_ring_depth<QP, true>(NW, NB);
   if (R == 0) return PMG_ERR_UNSUPPORTED_SHAPE;
   const size_t smem = (size_t)NW * CGeo<QP>::fwd_floats(R, NB) * sizeof(float);
@@ -622,9 +639,9 @@ static int launch_fwd_c(const FwdCParams& p, int n_groups, cudaStream_t st) {
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }
-template <int QP, int WT>
+template <int QP, int WT, int NW>
 static int launch_bwd_c(const BwdCParams& p, int n_groups, cudaStream_t st) {
-  constexpr int NW = 8, NB = 2;
+  constexpr int NB = 2;
   const int R = compact_ring_depth<QP, false>(NW, NB);
   if (R == 0) return PMG_ERR_UNSUPPORTED_SHAPE;
   const size_t smem = (size_t)NW * CGeo<QP>::bwd_floats(R, NB) * sizeof(float);
@@ -653,12 +670,18 @@ template <bool FWD, typename P>
 static int dispatch_compact(const P& p, const pmg_transition* tr, int n_groups, cudaStream_t st) {
   int QP, WT;
   compact_geometry(tr, QP, WT);
-#define PMG_CC(QPv, WTv)                                                        \
+  // 12 chains per CTA (3 warps per scheduler) when the plan has more chains than 8 per SM can hold at once
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool wide = n_groups > 8 * sms;
+#define PMG_CC(QPv, WTv, NWv)                                                   \
   if (QP == QPv && WT == WTv) {                                                 \
-    if constexpr (FWD) return launch_fwd_c<QPv, WTv>(p, n_groups, st);          \
-    else return launch_bwd_c<QPv, WTv>(p, n_groups, st);                        \
+    if constexpr (FWD) return launch_fwd_c<QPv, WTv, NWv>(p, n_groups, st);     \
+    else return launch_bwd_c<QPv, WTv, NWv>(p, n_groups, st);                   \
   }
-  PMG_CC(4, 5) PMG_CC(7, 5) PMG_CC(8, 5) PMG_CC(7, 10) PMG_CC(8, 10)
+  if (wide) { PMG_CC(7, 5, 12) PMG_CC(8, 5, 12) }
+  PMG_CC(4, 5, 8) PMG_CC(7, 5, 8) PMG_CC(8, 5, 8) PMG_CC(7, 10, 8) PMG_CC(8, 10, 8)
 #undef PMG_CC
   return PMG_ERR_UNSUPPORTED_SHAPE;
 }

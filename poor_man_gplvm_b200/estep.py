@@ -23,7 +23,9 @@ from .shard import TimeShard
 
 DEFAULT_HALO = int(os.environ.get("PMG_HALO", "256"))
 DEFAULT_SEAM_TOL = float(os.environ.get("PMG_SEAM_TOL", "1e-5"))
-MIN_CHUNK_OVER_HALO = int(os.environ.get("PMG_MIN_CHUNK_OVER_HALO", "3"))
+MIN_CHUNK_OVER_HALO = int(os.environ.get("PMG_MIN_CHUNK_OVER_HALO", "2"))
+# chains per SM of an EM-mode plan on the compact kernels (12 warps per CTA, 3 per scheduler); 8 elsewhere
+EM_CHAINS_PER_SM = int(os.environ.get("PMG_EM_CHAINS_PER_SM", "12"))
 
 
 def plan_chunks(n_core, halo, sm_count, chains_per_sm=8):
@@ -46,7 +48,8 @@ class EStep:
     """Buffers and launch plan for repeated E-steps over the same spike matrix (this rank's block)."""
 
     def __init__(self, y, op, ma_neuron=None, ma_latent=None, likelihood_scale=1.0, halo=None, seam_tol=None,
-                 chunk_len=None, emission_impl=0, shard=None):
+                 chunk_len=None, emission_impl=0, shard=None, em_mode=False):
+        """em_mode: the plan is sized for the compact EM kernels (more, shorter chains) when they apply."""
         self.op = op
         self.K = op.K
         self.dev = y.device
@@ -64,8 +67,11 @@ class EStep:
         self.T = y_ext.shape[0]
         self.core = slice(self.h_left, self.h_left + self.T_core)
         self.sm_count = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        self.compact_ok = (os.environ.get("PMG_SCAN_COMPACT", "1") != "0"
+                           and ops.scan_compact_supported(op, self.scale))
         if chunk_len is None:
-            chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count)
+            wide = em_mode and self.compact_ok and self.K > 31 * 8       # the 12-chain variants exist for K > 248
+            chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count, EM_CHAINS_PER_SM if wide else 8)
         self.chunk_len = int(min(max(1, chunk_len), self.T_core))
         self.plan = ops.make_plan(self.T, self.core.start, self.core.stop, self.chunk_len, self.halo,
                                   self.shard.is_first, self.shard.is_last, self.scale)
@@ -87,8 +93,6 @@ class EStep:
         self._alpha = None                 # [T,2,K] filtered posterior of the general path (allocated on first use)
         self._ax = None                    # [T,K+4] compact filtered posterior of the EM fast path
         self.lmr = torch.zeros(self.T, **f32)
-        self.compact_ok = (os.environ.get("PMG_SCAN_COMPACT", "1") != "0"
-                           and ops.scan_compact_supported(op, self.scale))
         self.fwd_end = torch.zeros((S, 2, self.K), **f32)       # true message at the last bin of each chain
         self.first_out = torch.zeros((2, self.K), **f32)        # true message at the first core bin
         self.halo_state = torch.zeros((S, 2, self.K), **f32)

@@ -9,6 +9,7 @@ reads them (``np.asarray(x)``, ``x[...]``, arithmetic through NumPy), like a jax
 """
 from __future__ import annotations
 
+import os
 import threading
 from concurrent.futures import ThreadPoolExecutor
 
@@ -33,8 +34,109 @@ def _staging():
     return _ring, _pool
 
 
-def to_numpy(t):
-    """Device tensor -> fresh NumPy array (pipelined through pinned staging for large tensors)."""
+def _copy_stream(dev):
+    cs = _stream.get(dev.index)
+    if cs is None:
+        cs = _stream[dev.index] = torch.cuda.Stream(device=dev)
+    return cs
+
+
+def to_device(a, device):
+    """NumPy array -> device tensor of the same dtype.  Large pageable arrays go through the pinned staging
+    ring: worker threads copy 32 MB pieces into pinned buffers while earlier pieces are in flight on a copy
+    stream (a plain pageable cudaMemcpy reaches ~11 GB/s on the B200 box; the ring several times that)."""
+    a = np.ascontiguousarray(a)
+    if a.nbytes < (8 << 20) or not a.flags.c_contiguous or os.environ.get("PMG_H2D_RING", "1") == "0":
+        return torch.as_tensor(a).to(device)
+    device = torch.device(device)
+    tdtype = torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype
+    out = torch.empty(a.shape, dtype=tdtype, device=device)
+    src = a.reshape(-1).view(np.uint8)
+    dst = out.view(-1).view(torch.uint8)
+    nbytes = a.nbytes
+    ring, pool = _staging()
+    cs = _copy_stream(device)
+    cs.wait_stream(torch.cuda.current_stream(device))
+    chunks = list(range(0, nbytes, _CHUNK))
+    fut = [None] * _NBUF
+    ev = [None] * _NBUF
+
+    def fill(b, lo, n):
+        if ev[b] is not None:
+            ev[b].synchronize()                  # the previous copy out of this staging buffer is done
+        np.copyto(ring[b][1][:n], src[lo:lo + n])
+
+    for i in range(len(chunks) + _NBUF - 1):
+        if i < len(chunks):
+            b, lo = i % _NBUF, chunks[i]
+            n = min(_CHUNK, nbytes - lo)
+            fut[b] = (pool.submit(fill, b, lo, n), lo, n)
+        j = i - (_NBUF - 1)
+        if 0 <= j < len(chunks):
+            b = j % _NBUF
+            f, lo, n = fut[b]
+            f.result()
+            with torch.cuda.stream(cs):
+                dst[lo:lo + n].copy_(ring[b][0][:n], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(cs)
+            ev[b] = e
+    torch.cuda.current_stream(device).wait_stream(cs)
+    for e in ev:
+        if e is not None:
+            e.synchronize()                      # the staging ring may be reused by the next call
+    return out
+
+
+_libc = None
+_MADV_POPULATE_WRITE = 23                        # Linux >= 5.14: fault the pages in (writable) without touching data
+
+
+def _touch(view):
+    """First-touch the pages of a uint8 view on this thread, with the GIL released (ctypes foreign call)."""
+    global _libc
+    import ctypes
+    if _libc is None:
+        _libc = ctypes.CDLL(None, use_errno=True)
+    addr = view.ctypes.data
+    end = addr + view.size
+    lo = addr & ~4095
+    rc = _libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(end - lo), ctypes.c_int(_MADV_POPULATE_WRITE))
+    if rc != 0:                                  # older kernel / unsupported mapping: write the bytes instead
+        ctypes.memset(ctypes.c_void_p(addr), 0, view.size)
+
+
+class HostBuffers:
+    """Result arrays allocated up front with their pages touched on background threads, so that the
+    first-touch page faults of the (multi-GB) outputs overlap the EM iterations instead of the final
+    device->host copies."""
+
+    def __init__(self, specs, threads=8):
+        self._pool = ThreadPoolExecutor(max_workers=threads)
+        self._arrays, self._futs = {}, {}
+        for name, shape, dtype in specs:
+            arr = np.empty(shape, dtype=dtype)
+            flat = arr.reshape(-1).view(np.uint8)
+            self._arrays[name] = arr
+            self._futs[name] = [self._pool.submit(_touch, flat[lo:lo + (64 << 20)])
+                                for lo in range(0, flat.size, 64 << 20)]
+
+    def take(self, name, shape=None):
+        """The prefaulted array (waits for its pages), or None if it was not planned with this shape."""
+        arr = self._arrays.pop(name, None)
+        if arr is None or (shape is not None and tuple(arr.shape) != tuple(shape)):
+            return None
+        for f in self._futs.pop(name):
+            f.result()
+        return arr
+
+    def close(self):
+        self._pool.shutdown(wait=False)
+
+
+def to_numpy(t, out=None):
+    """Device tensor -> NumPy array (pipelined through pinned staging for large tensors).
+    out: optional preallocated (ideally prefaulted) destination of the same shape and dtype."""
     if not isinstance(t, torch.Tensor):
         return np.asarray(t)
     if not t.is_cuda:
@@ -44,13 +146,13 @@ def to_numpy(t):
     if nbytes < (8 << 20):
         return t.cpu().numpy()
     ring, pool = _staging()
-    out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    np_dtype = torch.empty(0, dtype=t.dtype).numpy().dtype
+    if out is None or tuple(out.shape) != tuple(t.shape) or out.dtype != np_dtype or not out.flags.c_contiguous:
+        out = np.empty(tuple(t.shape), dtype=np_dtype)
     dst = out.reshape(-1).view(np.uint8)
     src = t.view(-1).view(torch.uint8)
     dev = t.device
-    cs = _stream.get(dev.index)
-    if cs is None:
-        cs = _stream[dev.index] = torch.cuda.Stream(device=dev)
+    cs = _copy_stream(dev)
     cs.wait_stream(torch.cuda.current_stream(dev))
     pending = [None] * _NBUF
 

@@ -7,6 +7,7 @@ back to torch ops or to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -116,7 +117,8 @@ class CountsF16:
         _f32(y, "y", 2)
         self.T, self.N = y.shape
         self.ones_col = bool(ones_col)
-        self.ld = (self.N + (1 if ones_col else 0) + 7) // 8 * 8
+        al = int(os.environ.get("PMG_Y16_ALIGN", "8"))              # experiment: 64 = 128-byte aligned rows
+        self.ld = (self.N + (1 if ones_col else 0) + al - 1) // al * al
         self.data = torch.empty((self.T, self.ld), dtype=torch.float16, device=y.device)
         self._inexact = torch.zeros(1, dtype=torch.int32, device=y.device)
         check(lib.pmg_counts_to_f16(self.T, self.N, _p(y), self.N, _p(self.data), self.ld, _p(self._inexact),
@@ -147,11 +149,14 @@ def emission_prepare_f16(tuning, y16, ma_neuron=None, dt=1.0):
         raise ValueError("y has %d neurons but tuning has %d" % (y16.N, N))
     bn = emission_tile_n(K)
     Kpad = (K + bn - 1) // bn * bn
-    L16 = torch.empty((2, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
+    brep = max(1, int(os.environ.get("PMG_EM_BREP", "1")))      # experiment: replicas of the operand
+    L16 = torch.empty((2 * brep, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
     lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
     check(lib.pmg_emission_prepare_f16(K, N, _p(tuning), _p(ma_neuron), float(dt), Kpad, y16.ld, _p(L16),
                                        _p(lam_sum), _stream()), "pmg_emission_prepare_f16")
     _count(1)
+    for r in range(1, brep):
+        L16[2 * r:2 * r + 2] = L16[:2]
     return L16, lam_sum
 
 

@@ -80,10 +80,12 @@ def test_move_operator_factorisation_reconstructs_P0(K, mv):
 def test_plan_chunks_bounds():
     from poor_man_gplvm_b200.estep import plan_chunks
     from poor_man_gplvm_b200.estep import MIN_CHUNK_OVER_HALO
-    assert plan_chunks(700, 256, 148) == 700                      # short sequences: one exact chain
+    assert plan_chunks(400, 256, 148) == 400                      # short sequences: one exact chain
     c = plan_chunks(10 ** 6, 256, 148)
     assert c >= MIN_CHUNK_OVER_HALO * 256 and (10 ** 6 + c - 1) // c <= 148 * 8
     assert (10 ** 6 + c - 1) // c > 148 * 7                       # the headline run fills every SM
+    c12 = plan_chunks(10 ** 6, 256, 148, 12)                      # EM-mode plan of the compact kernels
+    assert c12 >= MIN_CHUNK_OVER_HALO * 256 and 148 * 11 < (10 ** 6 + c12 - 1) // c12 <= 148 * 12
     assert plan_chunks(5000, 0, 148) == 5000
 
 
