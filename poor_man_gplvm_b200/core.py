@@ -46,6 +46,8 @@ class _Timing:
 
     def __init__(self):
         self.on = bool(os.environ.get("PMG_TIMING"))
+        self.per_iter = os.environ.get("PMG_TIMING") == "2"
+        self.iters = []
         self.t = time.perf_counter()
         self.marks = []
 
@@ -56,9 +58,19 @@ class _Timing:
             self.marks.append((name, now - self.t))
             self.t = now
 
+    def iteration(self):
+        """PMG_TIMING=2: wall time of every EM iteration (synchronised; perturbs the loop)."""
+        if self.per_iter:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.iters.append(now - self.t_it)
+            self.t_it = now
+
     def report(self):
         if self.on:
             print("fit_em timing: " + ", ".join("%s %.3fs" % m for m in self.marks), flush=True)
+        if self.per_iter:
+            print("fit_em iterations (ms): " + " ".join("%.1f" % (x * 1e3) for x in self.iters), flush=True)
 
 
 def _seed_from_key(key):
@@ -448,12 +460,6 @@ class PoissonGPLVMJump1D:
         T, K = int(np.shape(y_in)[0]), self.n_latent_bin
         y_dev = self._dev(y_in)                       # the one host->device copy of the spikes
         tm.mark("h2d_y")
-        # the host copies of the T-sized results are allocated now and their pages faulted in by background
-        # threads while the EM iterations run on the GPU
-        bufs = None
-        if not return_device and n_iter > 0 and T * K >= (1 << 22):
-            bufs = hostio.HostBuffers([("posterior", (T, 2, K), np.float32), ("latent", (T, K), np.float32),
-                                       ("dynamics", (T, 2), np.float32)])
         if save_every is None:
             save_every = n_iter
         P, logP, M, logM, op = self._transition_pack(hyperparam_)
@@ -484,6 +490,13 @@ class PoissonGPLVMJump1D:
         self.opt_state_init_fun = ops.AdamState
         W, state, es = loop.W, loop.state, loop.es
         tm.mark("setup")
+        # the host copies of the T-sized results are allocated now and their pages faulted in by background
+        # threads while the EM iterations run on the GPU (after the setup above: the populate calls hold the
+        # process's memory-map lock, which stalls every allocation the setup makes on the main thread)
+        bufs = None
+        if not return_device and n_iter > 0 and T * K >= (1 << 22):
+            bufs = hostio.HostBuffers([("posterior", (T, 2, K), np.float32), ("latent", (T, K), np.float32),
+                                       ("dynamics", (T, 2), np.float32)])
 
         lml_dev, m_hist = [], []
         saved = {'log_posterior_all_saved': [], 'params_saved': [], 'tuning_saved': [], 'iter_saved': [],
@@ -493,7 +506,9 @@ class PoissonGPLVMJump1D:
         # jax device arrays in the reference (core.py:672-675, :703): copied to the host on first use
         lazy_log = (lambda t: torch.log(t)) if return_device else (lambda t: hostio.LazyHostArray(t, torch.log))
         res = None
+        tm.t_it = time.perf_counter()
         for i in range(n_iter):
+            tm.iteration()
             last = i == n_iter - 1
             snap = (i % save_every == 0)
             res, m_res = loop.iteration(want_gamma=(last or snap), want_dyn=last, want_gamma_lat=last)
@@ -508,6 +523,7 @@ class PoissonGPLVMJump1D:
                 saved['log_marginal_saved'].append(res.log_marginal)
                 saved['iter_saved'].append(i)
 
+        tm.iteration()
         tm.mark("em_loop")
         lml_host = torch.stack(lml_dev).cpu().numpy().astype(np.float32) if lml_dev else np.zeros(0, np.float32)
         saved['log_marginal_saved'] = [np.float32(v.item()) for v in saved['log_marginal_saved']]

@@ -83,7 +83,7 @@ __global__ void emission_prepare_f16_kernel(int K, int N, const float* __restric
 // ---------------------------------------------------------------------------------------------
 struct EmissionTcParams {
   int64_t T;
-  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages, stagger, nostore, brep, brep_rows;
+  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages, stagger, nostore, ep_nbuf;
   uint32_t idesc, tmem_cols;
   const float* lam_sum;
   const float* lgam;
@@ -94,20 +94,38 @@ struct EmissionTcParams {
 
 constexpr int EM_PB = 2;   // fp16 pieces of loglam
 constexpr int EM_MI = 2;   // 128-row tiles per work unit: both share every right-hand tile fetched from L2
+constexpr int EP_BUF_BYTES = 4096;   // epilogue staging tile: 32 rows x 128 B
+constexpr int EM_THREADS = 384;      // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 / 8-11 epilogue
+
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
 
 // Work unit = 256 time bins x BN latent bins: two TMEM accumulators side by side, one pass over the neurons.
-// The kernel is bound by the L2 -> shared-memory feed of the (small, shared) right-hand operand, so a unit
-// uses each right-hand tile for two row tiles; the epilogue of accumulator 0 overlaps the first MMAs of the
-// next unit (per-accumulator "drained" barriers), the TMA producer keeps prefetching throughout.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// The main loop is bound by the L2 -> shared-memory feed of the (small, shared) right-hand operand, so a unit
+// uses each right-hand tile for two row tiles.  Epilogue: one set of four warps per accumulator; every warp
+// drains its 32 TMEM lanes in chunks of 32 columns -> registers (next chunk's load in flight) -> swizzled
+// staging tile -> TMA store (full 128-byte lines; rows past T and columns past K are clipped by the tensor
+// map).  An accumulator is handed back to the MMA warp as soon as its last chunk is in registers, and the MMA
+// warp starts a unit with the accumulator-0 products of the first two K blocks, so the stores and most of the
+// drain run under the next unit's MMAs.
+__global__ void __launch_bounds__(EM_THREADS, 1)
 emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
                    const EmissionTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = p.BN;
   const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* stg_base = smem + (size_t)p.stages * stage_bytes;                      // 1024-aligned
+  float* ls_s = reinterpret_cast<float*>(stg_base + (size_t)8 * p.ep_nbuf * EP_BUF_BYTES);   // [Kpad]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ls_s + ((p.Kpad + 3) & ~3));
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 1;
@@ -120,7 +138,18 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int b = 0; b < EM_MI; ++b) mbar_init(&tempty[b], 128);
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  // per-column term of the epilogue: sum_n lam (NaN marks a masked-out latent bin)
+  for (int k = threadIdx.x; k < p.Kpad; k += blockDim.x) {
+    float v = 0.f;
+    if (k < p.K) {
+      v = p.lam_sum[k];
+      if (p.ma_latent && p.ma_latent[k] == 0.f) v = __int_as_float(0x7fc00000);
+    }
+    ls_s[k] = v;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC32); tma_prefetch_desc(&tmC16);
+  }
   if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -149,7 +178,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int pc = 0; pc < EM_PB; ++pc)
             tma_load_2d(sA + EM_MI * TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kbe * TC_BK,
-                        p.brep_rows * (int)(blockIdx.x % p.brep) + pc * p.Kpad + nt * BN);
+                        pc * p.Kpad + nt * BN);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -157,29 +186,55 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
+      // all MMAs of K block `first` (first = this accumulator has nothing accumulated yet) for row tile mi
+      auto issue = [&](int st, int mi, bool first) {
+        const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(mi * BN);
+#pragma unroll
+        for (int pc = 0; pc < EM_PB; ++pc) {
+          const uint32_t sB = sA + EM_MI * TC_A_BYTES + pc * b_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sA + mi * TC_A_BYTES + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(sB + k * 32, 16, 1024);
+            mma_f16_ss(d_tmem, ad, bd, p.idesc, (first && pc == 0 && k == 0) ? 0u : 1u);
+          }
+        }
+      };
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
         const uint32_t drained = (uint32_t)(it & 1) ^ 1;      // parity of "the previous unit's epilogue is done"
-        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        int kb = 0;
+        if (p.n_kblocks >= 2 && p.stages >= 2) {
+          // accumulator 0 is drained first: run its products of the first two K blocks while accumulator 1 drains
+          const int s0 = stage; const uint32_t ph0 = phase;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          const int s1 = stage; const uint32_t ph1 = phase;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          mbar_wait(&full[s0], ph0);
+          mbar_wait(&tempty[0], drained);
+          tc_fence_after();
+          issue(s0, 0, true);
+          mbar_wait(&full[s1], ph1);
+          tc_fence_after();
+          issue(s1, 0, false);
+          mbar_wait(&tempty[1], drained);
+          tc_fence_after();
+          issue(s0, 1, true);
+          mma_commit(&empty[s0]);
+          issue(s1, 1, false);
+          mma_commit(&empty[s1]);
+          kb = 2;
+        }
+        for (; kb < p.n_kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
 #pragma unroll
           for (int mi = 0; mi < EM_MI; ++mi) {
             if (kb == 0) {
               mbar_wait(&tempty[mi], drained);
               tc_fence_after();
             }
-            const uint32_t d_tmem = tmem_base + (uint32_t)(mi * BN);
-#pragma unroll
-            for (int pc = 0; pc < EM_PB; ++pc) {
-              const uint32_t sB = sA + EM_MI * TC_A_BYTES + pc * b_bytes;
-#pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                const uint64_t ad = make_smem_desc(sA + mi * TC_A_BYTES + k * 32, 16, 1024);
-                const uint64_t bd = make_smem_desc(sB + k * 32, 16, 1024);
-                mma_f16_ss(d_tmem, ad, bd, p.idesc, (kb | pc | k) != 0);
-              }
-            }
+            issue(stage, mi, kb == 0);
           }
           mma_commit(&empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -189,50 +244,88 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp >= 4) {
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    int it = 0;
-    const bool vec_ok = (p.ldll & 3) == 0;
+    const int mi = (warp - 4) >> 2;              // accumulator (row tile) this warp set drains
+    const uint32_t stg = smem_u32(stg_base + (size_t)(warp - 4) * p.ep_nbuf * EP_BUF_BYTES);
+    const uint32_t ls_addr = smem_u32(ls_s);
+    const uint32_t stg_row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
+    const uint32_t stg_row64 = (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
+    const int nch = (BN + 31) / 32;              // chunks per accumulator (BN is a multiple of 16: the last may be 16 wide)
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mi * BN);
+    const bool masked = p.ma_latent != nullptr;
+    int it = 0, buf = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int mp = unit / p.n_ntiles, nt = unit % p.n_ntiles;
+      const int64_t t0 = (int64_t)(mp * EM_MI + mi) * TC_BM + q * 32;     // first row of this warp
+      const float lg = (t0 + lane) < p.T ? __ldg(p.lgam + t0 + lane) : 0.f;
+      const bool rows_ok = t0 < p.T && !p.nostore;
       mbar_wait(tfull, (uint32_t)(it & 1));
       tc_fence_after();
-      for (int mi = 0; mi < EM_MI; ++mi) {
-        const int64_t t = (int64_t)(mp * EM_MI + mi) * TC_BM + q * 32 + lane;
-        const bool t_ok = t < p.T;
-        const float lg = t_ok ? p.lgam[t] : 0.f;
-        float* orow = p.ll + (size_t)(t_ok ? t : 0) * p.ldll;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mi * BN);
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld_x16(taddr + c0, r);
-          tmem_ld_wait();
-          const int k0 = nt * BN + c0;
-          if (t_ok && k0 < p.K && !p.nostore) {
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int k = k0 + j;
-              float x = __uint_as_float(r[j]);
-              if (k < p.K) {
-                x = x - __ldg(p.lam_sum + k) - lg;
-                if (p.ma_latent && __ldg(p.ma_latent + k) == 0.f) x = kVeryNegLL;
-              }
-              v[j] = x;
-            }
-            if (vec_ok && k0 + 16 <= p.K) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(orow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (k0 + j < p.K) orow[k0 + j] = v[j];
-            }
-          }
+
+      auto issue = [&](int c, uint32_t (&r)[32]) {
+        const int c0 = c * 32;
+        if (c0 + 32 <= BN) tmem_ld_x32(tbase + (uint32_t)c0, r); else tmem_ld_x16_of32(tbase + (uint32_t)c0, r);
+      };
+      auto process = [&](int c, uint32_t (&r)[32]) {
+        const int c0 = c * 32;
+        if (c == nch - 1) {                      // the last chunk of this accumulator has left TMEM
+          tc_fence_before();
+          mbar_arrive(&tempty[mi]);
         }
-        tc_fence_before();
-        mbar_arrive(&tempty[mi]);                // accumulator mi may be overwritten by the next unit
+        const bool wide = c0 + 32 <= BN;
+        // the staging tile about to be overwritten must have been read by its TMA store
+        if (lane == 0) {
+          if (p.ep_nbuf == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+        }
+        __syncwarp();
+        const uint32_t sb = stg + (uint32_t)buf * EP_BUF_BYTES;
+        const uint32_t lsp = ls_addr + (uint32_t)(nt * BN + c0) * 4u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!wide && j >= 4) break;
+          const float4 l4 = lds_f4(lsp + 16u * j);
+          float4 v;
+          v.x = __uint_as_float(r[4 * j + 0]) - l4.x - lg;
+          v.y = __uint_as_float(r[4 * j + 1]) - l4.y - lg;
+          v.z = __uint_as_float(r[4 * j + 2]) - l4.z - lg;
+          v.w = __uint_as_float(r[4 * j + 3]) - l4.w - lg;
+          if (masked) {
+            if (l4.x != l4.x) v.x = kVeryNegLL;
+            if (l4.y != l4.y) v.y = kVeryNegLL;
+            if (l4.z != l4.z) v.z = kVeryNegLL;
+            if (l4.w != l4.w) v.w = kVeryNegLL;
+          }
+          const uint32_t off = wide ? stg_row128 + (((uint32_t)j ^ sw128) << 4)
+                                    : stg_row64 + (((uint32_t)j ^ sw64) << 4);
+          sts_f4(sb + off, v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int col0 = nt * BN + c0;
+          if (rows_ok && col0 < p.K) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(wide ? &tmC32 : &tmC16)), "r"(sb), "r"(col0), "r"((int)t0)
+                         : "memory");
+          }
+          bulk_commit();
+        }
+        if (++buf == p.ep_nbuf) buf = 0;
+      };
+
+      uint32_t ra[32], rb[32];
+      issue(0, ra);
+      for (int c = 0; c < nch; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nch) issue(c + 1, rb);
+        process(c, ra);
+        if (c + 1 < nch) {
+          tmem_ld_wait();
+          if (c + 2 < nch) issue(c + 2, ra);
+          process(c + 1, rb);
+        }
       }
     }
+    if (lane == 0) bulk_wait_read<0>();          // shared memory must outlive the last stores' reads
   }
   tc_fence_before();
   __syncthreads();
@@ -283,8 +376,7 @@ emission_tc_kernel_v1(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_load_2d(sA, &tmA, &full[stage], kbe * TC_BK, mt * TC_BM);
 #pragma unroll
           for (int pc = 0; pc < EM_PB; ++pc)
-            tma_load_2d(sA + TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kbe * TC_BK,
-                        p.brep_rows * (int)(blockIdx.x % p.brep) + pc * p.Kpad + nt * BN);
+            tma_load_2d(sA + TC_A_BYTES + pc * b_bytes, &tmB, &full[stage], kbe * TC_BK, pc * p.Kpad + nt * BN);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -425,10 +517,7 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   CUtensorMap tmA, tmB;
   int rc = make_tmap_f16(&tmA, y16, (uint64_t)T, (uint64_t)ld16, (uint64_t)ld16, TC_BM);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
-  // experiment knob PMG_EM_BREP=r: the caller provides r identical copies of the right-hand operand back to back
-  static const int brep_avail = std::getenv("PMG_EM_BREP") ? std::atoi(std::getenv("PMG_EM_BREP")) : 1;
-  rc = make_tmap_f16(&tmB, loglam16, (uint64_t)EM_PB * Kpad * (brep_avail > 0 ? brep_avail : 1), (uint64_t)ld16,
-                     (uint64_t)ld16, (uint32_t)BN);
+  rc = make_tmap_f16(&tmB, loglam16, (uint64_t)EM_PB * Kpad, (uint64_t)ld16, (uint64_t)ld16, (uint32_t)BN);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
 
   EmissionTcParams p;
@@ -436,44 +525,71 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   p.n_kblocks = (int)((ld16 + TC_BK - 1) / TC_BK);
   p.n_mtiles = (int)((T + TC_BM - 1) / TC_BM);
   p.n_ntiles = n_ntiles;
-  static const int kver = std::getenv("PMG_EM_KERNEL") ? std::atoi(std::getenv("PMG_EM_KERNEL")) : 1;
+  // experiment knobs (environment): PMG_EM_KERNEL=1 forces the single-tile kernel, PMG_EM_NOSTORE=1 drops the
+  // stores (timing only), PMG_EM_STAGES caps the pipeline depth, PMG_EM_STAGGER=0 disables the K-block rotation
+  static const int kver_env = std::getenv("PMG_EM_KERNEL") ? std::atoi(std::getenv("PMG_EM_KERNEL")) : 2;
   static const int nostore = std::getenv("PMG_EM_NOSTORE") ? std::atoi(std::getenv("PMG_EM_NOSTORE")) : 0;
-  static const int brep = std::getenv("PMG_EM_BREP") ? std::atoi(std::getenv("PMG_EM_BREP")) : 1;
-  p.nostore = nostore;
-  p.brep = brep_avail > 0 && brep <= brep_avail ? brep : 1;
-  p.brep_rows = EM_PB * Kpad;
-  const uint32_t stage_bytes = (kver == 2 ? EM_MI : 1) * TC_A_BYTES + EM_PB * BN * TC_BK * 2;
-  // 227 KB of shared memory per CTA minus alignment slack and barriers
-  int stages = (int)((225 * 1024) / stage_bytes);
-  // measured on B200 at the headline shape: 2 stages 1.95 ms, 3 stages 2.08 ms (the loads of all CTAs hit the
-  // same L2 lines of the small right-hand operand; deeper prefetch only adds contention)
-  static const int st_env = std::getenv("PMG_EM_STAGES") ? std::atoi(std::getenv("PMG_EM_STAGES")) : 2;
-  if (st_env > 0 && stages > st_env) stages = st_env;
-  if (stages > 8) stages = 8;
-  if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
-  p.stages = stages;
+  static const int st_env = std::getenv("PMG_EM_STAGES") ? std::atoi(std::getenv("PMG_EM_STAGES")) : 0;
   static const int stagger_env = std::getenv("PMG_EM_STAGGER") ? std::atoi(std::getenv("PMG_EM_STAGGER")) : 1;
+  p.nostore = nostore;
   p.stagger = stagger_env;
   p.idesc = make_idesc_f16(TC_BM, BN, 0, 0, 0);
   p.tmem_cols = pow2_cols(2 * BN);
   p.lam_sum = lam_sum; p.lgam = lgam; p.ma_latent = ma_latent; p.ll = ll; p.ldll = ldll;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  p.ep_nbuf = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   PMG_CUDA_CHECK(cudaGetDevice(&dev));
   PMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (kver != 2) {
+  const size_t smem_max = 227 * 1024;
+
+  // 256-row work units + TMA-store epilogue: needs 16-byte aligned rows of ll
+  bool paired = kver_env != 1 && (ldll & 3) == 0 && ((uintptr_t)ll & 15) == 0;
+  if (paired) {
+    const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * BN * TC_BK * 2;
+    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (size_t)((Kpad + 3) & ~3) * sizeof(float);
+    int nbuf = 2;
+    int stages = 0;
+    for (; nbuf >= 1; --nbuf) {
+      const size_t stg_bytes = (size_t)8 * nbuf * EP_BUF_BYTES;
+      stages = fixed + stg_bytes < smem_max ? (int)((smem_max - fixed - stg_bytes) / stage_bytes) : 0;
+      if (stages >= 2) break;
+    }
+    if (stages < 2) {
+      paired = false;
+    } else {
+      if (stages > 6) stages = 6;
+      if (st_env > 0 && stages > st_env && st_env >= 2) stages = st_env;
+      p.stages = stages;
+      p.ep_nbuf = nbuf;
+      CUtensorMap tmC32, tmC16;
+      rc = make_tmap_f32(&tmC32, ll, (uint64_t)T, (uint64_t)K, (uint64_t)ldll, 32, 32);
+      if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+      rc = make_tmap_f32(&tmC16, ll, (uint64_t)T, (uint64_t)K, (uint64_t)ldll, 32, 16);
+      if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+      const size_t smem = (size_t)stages * stage_bytes + (size_t)8 * nbuf * EP_BUF_BYTES + fixed;
+      PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int n_units = ((p.n_mtiles + EM_MI - 1) / EM_MI) * p.n_ntiles;
+      emission_tc_kernel<<<n_units < sms ? n_units : sms, EM_THREADS, smem, st>>>(tmA, tmB, tmC32, tmC16, p);
+      PMG_LAUNCH_CHECK();
+      return PMG_OK;
+    }
+  }
+  // single-tile kernel with direct stores (any row pitch)
+  {
+    const uint32_t stage_bytes = TC_A_BYTES + EM_PB * BN * TC_BK * 2;
+    int stages = (int)((225 * 1024) / stage_bytes);
+    // measured on B200 at the headline shape: 2 stages 1.95 ms, 3 stages 2.08 ms
+    const int cap = st_env > 0 ? st_env : 2;
+    if (stages > cap) stages = cap;
+    if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = p.n_mtiles * p.n_ntiles;
     emission_tc_kernel_v1<<<n_tiles < sms ? n_tiles : sms, TC_THREADS, smem, st>>>(tmA, tmB, p);
     PMG_LAUNCH_CHECK();
-    return PMG_OK;
   }
-  const int n_units = ((p.n_mtiles + EM_MI - 1) / EM_MI) * p.n_ntiles;
-  const int grid = n_units < sms ? n_units : sms;
-  emission_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
-  PMG_LAUNCH_CHECK();
   return PMG_OK;
 }
 

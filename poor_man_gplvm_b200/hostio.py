@@ -89,11 +89,17 @@ def to_device(a, device):
 
 
 _libc = None
+_MADV_HUGEPAGE = 14
 _MADV_POPULATE_WRITE = 23                        # Linux >= 5.14: fault the pages in (writable) without touching data
+_TOUCH_PIECE = int(os.environ.get("PMG_TOUCH_PIECE_MB", "4")) << 20
 
 
 def _touch(view):
-    """First-touch the pages of a uint8 view on this thread, with the GIL released (ctypes foreign call)."""
+    """First-touch the pages of a uint8 view on this thread, with the GIL released (ctypes foreign calls).
+    The populate calls are issued in small pieces: each holds the process's memory-map lock for reading, and a
+    long hold stalls every mmap/munmap of the main thread (allocator traffic of the EM loop) behind it
+    (measured on the B200 box, fit_em at the headline size: 64 MB pieces 0.45 s, 4 MB pieces 0.31 s; transparent
+    huge pages make the populate slower, not faster)."""
     global _libc
     import ctypes
     if _libc is None:
@@ -101,9 +107,15 @@ def _touch(view):
     addr = view.ctypes.data
     end = addr + view.size
     lo = addr & ~4095
-    rc = _libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(end - lo), ctypes.c_int(_MADV_POPULATE_WRITE))
-    if rc != 0:                                  # older kernel / unsupported mapping: write the bytes instead
-        ctypes.memset(ctypes.c_void_p(addr), 0, view.size)
+    if os.environ.get("PMG_TOUCH_HUGEPAGE", "0") != "0":
+        _libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(end - lo), ctypes.c_int(_MADV_HUGEPAGE))
+    while lo < end:
+        n = min(_TOUCH_PIECE, end - lo)
+        rc = _libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(n), ctypes.c_int(_MADV_POPULATE_WRITE))
+        if rc != 0:                              # older kernel / unsupported mapping: write the bytes instead
+            a = max(lo, addr)
+            ctypes.memset(ctypes.c_void_p(a), 0, lo + n - a)
+        lo += n
 
 
 class HostBuffers:

@@ -1,0 +1,19 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+r() { env "$@" timeout 120 python scripts/bench_emission.py 2>&1 | tail -1; }
+r TAG=v3p
+r TAG=v3p_nostore PMG_EM_NOSTORE=1
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -k "emission or naive" > gpurun_out/pytest_i1.log 2>&1; echo "kernel tests rc=$?"
+tail -3 gpurun_out/pytest_i1.log
+timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --no-decode > gpurun_out/bench_i.json 2> gpurun_out/bench_i.err; echo "bench rc=$?"
+tail -3 gpurun_out/bench_i.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_i.json').read().strip().splitlines()[-1])
+print(round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['phases_ms_per_step'].items()})
+print('host', {k:round(v,3) for k,v in d['phases_host_ms_per_step'].items()})
+print(d['clocks'])
+PY
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"emission_tc_kernel" --launch-skip 2 -c 1 \
+   -o gpurun_out/prof_i_em -f python scripts/bench_emission.py > gpurun_out/ncu_i.log 2>&1; echo "ncu rc=$?"
