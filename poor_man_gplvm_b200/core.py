@@ -46,14 +46,16 @@ class _Timing:
 
     def __init__(self):
         self.on = bool(os.environ.get("PMG_TIMING"))
-        self.per_iter = os.environ.get("PMG_TIMING") == "2"
+        self.per_iter = os.environ.get("PMG_TIMING") in ("2", "3")
+        self.nosync = os.environ.get("PMG_TIMING") == "3"       # host-side marks only (no perturbation)
         self.iters = []
         self.t = time.perf_counter()
         self.marks = []
 
     def mark(self, name):
         if self.on:
-            torch.cuda.synchronize()
+            if not self.nosync:
+                torch.cuda.synchronize()
             now = time.perf_counter()
             self.marks.append((name, now - self.t))
             self.t = now
@@ -61,7 +63,8 @@ class _Timing:
     def iteration(self):
         """PMG_TIMING=2: wall time of every EM iteration (synchronised; perturbs the loop)."""
         if self.per_iter:
-            torch.cuda.synchronize()
+            if not self.nosync:
+                torch.cuda.synchronize()
             now = time.perf_counter()
             self.iters.append(now - self.t_it)
             self.t_it = now
@@ -128,6 +131,9 @@ class EMLoop:
                         em_mode=True)
         self.shard = self.es.shard
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
+        self._n_mstep = 0
+        self._hist = self._new_hist_block()
+        self._tuning = torch.empty((self.Phi.shape[0], model.n_neuron), dtype=torch.float32, device=self.W.device)
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
         self.use_tc = self.es.y16 is not None and self.es.y16.exact
         T_core, K = y_dev.shape[0], op.K
@@ -151,8 +157,29 @@ class EMLoop:
                 self.gamma_lat = gamma_lat
                 self.tw = gamma_lat.sum(dim=0, dtype=torch.float64).to(torch.float32)
 
+    _HIST_BLOCK = 32
+
+    def _mstep_out(self):
+        """Output buffers of the next M-step.  Nothing that outlives an iteration is allocated per iteration:
+        a device allocation that misses the caching allocator is a driver call behind the process's memory-map
+        lock, which fit_em's background page-population of the host result buffers holds most of the time
+        (measured: sporadic 40-180 ms stalls of single EM iterations).  The tuning buffer is reused every
+        iteration; the Adam histories live in blocks of _HIST_BLOCK iterations."""
+        slot = self._n_mstep % self._HIST_BLOCK
+        if slot == 0 and self._n_mstep > 0:
+            self._hist = self._new_hist_block()
+        self._n_mstep += 1
+        lh, eh, ni, fin = self._hist
+        return lh[slot], eh[slot], ni[slot:slot + 1], fin[slot], self._tuning
+
+    def _new_hist_block(self):
+        dev, n, mi = self.W.device, self._HIST_BLOCK, int(self.maxiter)
+        return (torch.empty((n, mi), dtype=torch.float32, device=dev), torch.empty((n, mi), dtype=torch.float32, device=dev),
+                torch.empty(n, dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.float32, device=dev))
+
     def iteration(self, want_gamma=False, want_dyn=False, want_gamma_lat=False):
-        """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path)."""
+        """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path).
+        The returned tuning (m_res[4]) is a buffer that the next iteration overwrites."""
         if self.use_tc:
             # reference core.py:807; the ones column of the fp16 counts makes column N = sum_t gamma
             stats = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)
@@ -163,7 +190,7 @@ class EMLoop:
         self.shard.allreduce_sum_(yw, self.tw)                      # time-sharded ranks: one packed all-reduce
         ops.phase("stats")
         m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
-                               self.maxiter, self.tol)             # reference core.py:810
+                               self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
         ops.phase("mstep")
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16)
@@ -519,7 +546,7 @@ class PoissonGPLVMJump1D:
             if snap:
                 saved['log_posterior_all_saved'].append(lazy_log(res.gamma))
                 saved['params_saved'].append(conv(W.clone()))
-                saved['tuning_saved'].append(conv(tuning))
+                saved['tuning_saved'].append(conv(tuning.clone() if return_device else tuning))
                 saved['log_marginal_saved'].append(res.log_marginal)
                 saved['iter_saved'].append(i)
 

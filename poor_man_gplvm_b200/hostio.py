@@ -123,7 +123,8 @@ class HostBuffers:
     first-touch page faults of the (multi-GB) outputs overlap the EM iterations instead of the final
     device->host copies."""
 
-    def __init__(self, specs, threads=8):
+    def __init__(self, specs, threads=None):
+        threads = threads or int(os.environ.get("PMG_TOUCH_THREADS", "8"))
         self._pool = ThreadPoolExecutor(max_workers=threads)
         self._arrays, self._futs = {}, {}
         for name, shape, dtype in specs:

@@ -501,9 +501,10 @@ class AdamState:
 
 
 def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, tol=1e-6, min_iters=5,
-               b1=0.9, b2=0.999, eps=1e-8):
+               b1=0.9, b2=0.999, eps=1e-8, out=None):
     """Runs the whole Adam loop on the device.  W and state are updated in place.
-    Returns device tensors (loss_hist[maxiter], err_hist[maxiter], n_iter[1] int32, final[2], tuning[K,N])."""
+    Returns device tensors (loss_hist[maxiter], err_hist[maxiter], n_iter[1] int32, final[2], tuning[K,N]);
+    out: optional tuple of preallocated tensors of those shapes to write into."""
     lib = _lib.load()
     _f32(Phi, "Phi", 2); _f32(yw, "yw", 2); _f32(tw, "tw", 1); _f32(W, "W", 2)
     K, B = Phi.shape
@@ -512,11 +513,19 @@ def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, t
         raise ValueError("inconsistent M-step shapes")
     dev = W.device
     maxiter = int(maxiter)
-    loss_hist = torch.empty(maxiter, dtype=torch.float32, device=dev)
-    err_hist = torch.empty(maxiter, dtype=torch.float32, device=dev)
-    n_iter = torch.empty(1, dtype=torch.int32, device=dev)
-    final = torch.empty(2, dtype=torch.float32, device=dev)
-    tuning = torch.empty((K, N), dtype=torch.float32, device=dev)
+    if out is not None:
+        loss_hist, err_hist, n_iter, final, tuning = out
+        if (loss_hist.numel() != maxiter or err_hist.numel() != maxiter or n_iter.numel() != 1 or final.numel() != 2
+                or tuple(tuning.shape) != (K, N) or n_iter.dtype != torch.int32
+                or not all(t.is_contiguous() for t in out)):
+            raise ValueError("mstep_adam: out buffers have the wrong shape")
+        _f32(loss_hist, "loss_hist"); _f32(err_hist, "err_hist"); _f32(final, "final"); _f32(tuning, "tuning", 2)
+    else:
+        loss_hist = torch.empty(maxiter, dtype=torch.float32, device=dev)
+        err_hist = torch.empty(maxiter, dtype=torch.float32, device=dev)
+        n_iter = torch.empty(1, dtype=torch.int32, device=dev)
+        final = torch.empty(2, dtype=torch.float32, device=dev)
+        tuning = torch.empty((K, N), dtype=torch.float32, device=dev)
     nbytes = lib.pmg_mstep_workspace_bytes(K, B, N, maxiter)
     ws = _workspace(nbytes, dev)
     check(lib.pmg_mstep_adam(K, B, N, _p(Phi), _p(yw), _p(tw), float(prior_std), float(step_size), float(b1),
