@@ -47,6 +47,24 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the hot kernels from the committed ncu --set full summary (headline workload)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_summary_v3.csv")
+    out = {}
+    try:
+        import csv
+        with open(path) as f:
+            for rec in csv.DictReader(f):
+                def gb(x):
+                    v, u = x.split()
+                    return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                name = rec["kernel"].replace("void ", "").split("(")[0].split("<")[0]
+                out[name] = gb(rec["dram__bytes_read.sum"]) + gb(rec["dram__bytes_write.sum"])
+    except Exception:
+        return {}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -310,14 +328,24 @@ def run_ours(args):
     pk = peaks()
     S = max(1, timer.n_begin)
     per = {k: v / S for k, v in phases.items()}     # ms per EM iteration per phase (second, instrumented pass)
+    # Algorithmic amounts per launch.  Scans: the compulsory HBM bytes of the kernel variant
+    # that ran.  EM-mode (compact) kernels: forward reads ll (4K) and writes the compact filtered posterior
+    # (4K+16 per bin); backward reads ll and that buffer and writes the fp16 hi/lo pieces of gamma_lat (4K):
+    # 8K and 12K bytes per bin.  General kernels (and SURVEY.md section 8(d)'s reference layout): 12K and 20K
+    # bytes per bin -- reported beside as "survey_bytes".  GEMMs: one fp32-equivalent GEMM, 2*T*N*K flop.
+    compact = bool(loop.es.compact_ok and loop.use_tc)
     algo = {
-        "forward": ("hbm", 12.0 * K * T),           # read ll 4K, write alpha 8K   bytes per bin
-        "backward": ("hbm", 16.0 * K * T),          # read ll 4K + alpha 8K, write gamma_lat 4K
-        "emission": ("tensor", 2.0 * T * N * K),
-        "stats": ("tensor", 2.0 * T * N * K),
+        "forward": ("hbm", (8.0 * K + 16.0) * T if compact else 12.0 * K * T, 12.0 * K * T),
+        "backward": ("hbm", 12.0 * K * T if compact else 16.0 * K * T, 20.0 * K * T),
+        "emission": ("tensor", 2.0 * T * N * K, None),
+        "stats": ("tensor", 2.0 * T * N * K, None),
     }
+    kernel_of = {"forward": "fwd_c_kernel" if compact else "fwd_bulk_kernel",
+                 "backward": "bwd_c_kernel" if compact else "bwd_bulk_kernel",
+                 "emission": "emission_tc_kernel", "stats": "atb_tc_kernel"}
+    traffic = ncu_traffic() if (args.workload == "headline" and not args.bins) else {}
     roof_all = {}
-    for name, (bound, amount) in algo.items():
+    for name, (bound, amount, survey) in algo.items():
         if name not in per or per[name] <= 0:
             continue
         sec = per[name] * 1e-3
@@ -327,12 +355,18 @@ def run_ours(args):
             # fp32-equivalent GEMM flops against the derived TF32 dense peak = measured bf16 / 2
             ach, peak, unit = amount / sec / 1e12, pk["bf16_tflops_sustained"] / 2.0, "TFLOP/s"
         roof_all[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                          "ms": per[name]}
+                          "ms": per[name], "kernel": kernel_of[name], "algorithmic": amount,
+                          "traffic": traffic.get(kernel_of[name])}
+        if survey is not None:
+            roof_all[name]["survey_bytes"] = survey
     dominant = max((k for k in roof_all), key=lambda k: roof_all[k]["ms"]) if roof_all else None
     roofline = None
     if dominant:
         r = dict(roof_all[dominant])
-        r.update({"kernel": dominant, "traffic": None, "peak_source": pk["src"]})
+        r.update({"phase": dominant, "peak_source": pk["src"],
+                  "traffic_source": "profiles/r01_ncu_full_summary_v3.csv (dram__bytes_read.sum + dram__bytes_write.sum "
+                                    "of one ncu --set full capture of this kernel at this workload)"
+                                    if r.get("traffic") else None})
         roofline = r
 
     # ---- end-to-end through the public API with host buffers (rank-local block; same n_iter per rank)
