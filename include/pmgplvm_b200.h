@@ -125,7 +125,11 @@ typedef struct pmg_scan_plan {
  * warm_in:  message a warm-up starts from: one [2,K] vector (warm_stride 0, e.g. the stationary
  *           distribution of the prior chain) or one per chain (warm_stride 2K: the previous EM
  *           iteration's message at that bin); NULL = uniform.  warm_out: [n_chain,2,K] or NULL,
- *           receives the message at each chain's warm-up start for the next pass. */
+ *           receives the message at each chain's warm-up start for the next pass (forward: chain c writes
+ *           slot c+1; backward: chain c writes slot c-1).  Time-sharded blocks: when right_exact == 0 the
+ *           forward pass also writes slot n_chain (the right neighbour's first chain) and when left_exact == 0
+ *           the backward pass also writes slot -1 (the left neighbour's last chain): the caller provides the
+ *           extra slot (forward: [n_chain+1,2,K]; backward: pass a pointer to slot 1 of [n_chain+1,2,K]). */
 int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
                 const float* carry_in, const float* warm_in, int64_t warm_stride, float* warm_out,
                 float* alpha, float* lmr, float* halo_state, int mode,
@@ -143,8 +147,9 @@ int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const floa
                  void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo, float* beta_end,
                  int mode, const int* chain_ids, int n_ids, pmg_stream_t stream);
 
-/* err[i] = max relative difference between est[i,:] and truth[i,:] over entries > floor.
- * est/truth are [n, len] with row strides in elements (truth rows may live inside alpha). */
+/* err[i] = max relative difference between est[i,:]/sum(est[i,:]) and truth[i,:]/sum(truth[i,:]) over entries
+ * whose normalised value is > floor (messages are defined up to a positive scale: every step of both passes
+ * renormalises).  est/truth are [n, len] with row strides in elements (truth rows may live inside alpha). */
 int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, const float* truth,
                    int64_t ld_truth, float floor_val, float* err, pmg_stream_t stream);
 /* EM-iteration fast path of the two passes ("compact" filtered posterior).  The filtered jump-state
@@ -188,6 +193,15 @@ int pmg_split_f16(int64_t T, int K, const float* src, int64_t lds, void* dst16, 
 int64_t pmg_atb_f16_workspace_bytes(int64_t T, int K, int N);
 int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
                 float* yw, void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
+
+/* Time reduction with BOTH operands split into two bf16 pieces ([2, T, ld], hi then lo; 16 significant bits,
+ * fp32 exponent range): out[k,n] = sum_t G[t,k] * Y[t,n] as three tensor-core products (hi*hi + hi*lo + lo*hi)
+ * accumulated in fp32; relative error ~2^-16 per term.  Used for the transition counts (SURVEY S4,
+ * decoder.py:215-221: G = alpha [T,2K], Y = r shifted by one bin).  ld % 8 == 0, 16-byte aligned pointers;
+ * workspace: pmg_atb_f16_workspace_bytes(T, K, N). */
+int pmg_split_bf16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16, pmg_stream_t stream);
+int pmg_atb_bf16x2(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
+                   float* out, void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
 
 /* log_acc[d,d',x,x'] = logM[d,d'] + logP_{d'}[x,x'] + log G[(d,x),(d',x')]   (G = alpha^T r, [2K,2K]):
  * decoder.py:221's accumulator; using the analytic log kernel keeps deep tails finite.

@@ -64,6 +64,9 @@ SIGNATURES = {
                                        C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_void_p, C.c_int64,
                                        c_f32p, c_f32p, C.c_int, c_i32p, C.c_int, c_stream]),
     "pmg_split_f16": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, C.c_void_p, C.c_int64, c_stream]),
+    "pmg_split_bf16": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, C.c_void_p, C.c_int64, c_stream]),
+    "pmg_atb_bf16x2": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_f32p,
+                                 C.c_void_p, C.c_int64, c_stream]),
     "pmg_atb_f16_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "pmg_atb_f16": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_f32p,
                               C.c_void_p, C.c_int64, c_stream]),

@@ -342,7 +342,10 @@ class PoissonGPLVMJump1D:
         c = res.core
         hi = c.stop - 1 if es.shard.is_last else c.stop          # pairs (t, t+1) with t in [c.start, hi)
         if hi > c.start:
-            G = ops.atb(res.alpha_ext.view(-1, 2 * K)[c.start:hi], res.r_ext.view(-1, 2 * K)[c.start + 1:hi + 1])
+            A = res.alpha_ext.view(-1, 2 * K)[c.start:hi]
+            R = res.r_ext.view(-1, 2 * K)[c.start + 1:hi + 1]
+            # long recordings: tensor cores on bf16 hi/lo pieces (three products); short ones: fp32 CUDA cores
+            G = ops.atb_bf16x2(A, R) if hi - c.start >= ops.XI_TC_MIN_BINS else ops.atb(A, R)
         else:
             G = torch.zeros((2 * K, 2 * K), dtype=torch.float32, device=self.device)
         es.shard.allreduce_sum_(G)

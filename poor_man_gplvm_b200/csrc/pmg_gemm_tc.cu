@@ -14,6 +14,7 @@
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
 #include "pmg_common.cuh"
 #include "pmg_tc.cuh"
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace pmg {
@@ -613,9 +614,12 @@ struct AtbTcParams {
 // One CTA owns TWO 128-neuron row tiles (two TMEM accumulators side by side) for one tile of latent bins and
 // one time split, so that every posterior tile fetched from L2 feeds 256 output rows: the kernel is bound by
 // the L2 -> shared-memory feed, not by the tensor pipe.
+// PA = pieces of the row-side operand (1: exact fp16 counts; 2: hi/lo pieces, products hi*hi + hi*lo + lo*hi),
+// FMT = 0 fp16, 1 bf16.
+template <int PA, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG,
-              const AtbTcParams p) {
+atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY1,
+              const __grid_constant__ CUtensorMap tmG, const AtbTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int mp = blockIdx.x, nt = blockIdx.y, sp = blockIdx.z;
@@ -625,8 +629,8 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   bn = (bn + 63) / 64 * 64;
   if (bn > p.BN) bn = p.BN;
   const int n_boxes_b = bn / 64;
-  const uint32_t a_tile_bytes = 2 * AT_BOX_BYTES;              // 128 neurons x 32 time bins
-  const uint32_t a_bytes = 2 * a_tile_bytes;
+  const uint32_t a_tile_bytes = 2 * AT_BOX_BYTES;              // 128 neurons x 32 time bins (one piece)
+  const uint32_t a_bytes = 2 * PA * a_tile_bytes;
   const uint32_t b_piece_bytes = (uint32_t)(p.BN / 64) * AT_BOX_BYTES;
   const uint32_t stage_bytes = a_bytes + AT_PG * b_piece_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -651,7 +655,7 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   int64_t t_end = t_begin + p.t_per_split;
   if (t_end > p.T) t_end = p.T;
   const int n_tb = t_end > t_begin ? (int)((t_end - t_begin + AT_BKT - 1) / AT_BKT) : 0;
-  const uint32_t tx_bytes = (uint32_t)n_mi * a_tile_bytes + AT_PG * (uint32_t)n_boxes_b * AT_BOX_BYTES;
+  const uint32_t tx_bytes = (uint32_t)(n_mi * PA) * a_tile_bytes + AT_PG * (uint32_t)n_boxes_b * AT_BOX_BYTES;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -663,8 +667,13 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         mbar_arrive_expect_tx(&full[stage], tx_bytes);
         for (int mi = 0; mi < n_mi; ++mi) {
           const int m0 = (2 * mp + mi) * TC_BM;
-          tma_load_2d(sA + mi * a_tile_bytes, &tmY, &full[stage], m0, t0);
-          tma_load_2d(sA + mi * a_tile_bytes + AT_BOX_BYTES, &tmY, &full[stage], m0 + 64, t0);
+#pragma unroll
+          for (int pa = 0; pa < PA; ++pa) {       // one tensor map per piece: rows past T are zero-filled
+            const CUtensorMap* tm = pa == 0 ? &tmY : &tmY1;
+            uint8_t* dst = sA + (mi * PA + pa) * a_tile_bytes;
+            tma_load_2d(dst, tm, &full[stage], m0, t0);
+            tma_load_2d(dst + AT_BOX_BYTES, tm, &full[stage], m0 + 64, t0);
+          }
         }
         for (int pc = 0; pc < AT_PG; ++pc)
           for (int b = 0; b < n_boxes_b; ++b)
@@ -675,7 +684,7 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(TC_BM, bn, 1, 1, 0);
+      const uint32_t idesc = make_idesc_f16(TC_BM, bn, 1, 1, FMT);
       int stage = 0; uint32_t phase = 0;
       for (int tb = 0; tb < n_tb; ++tb) {
         mbar_wait(&full[stage], phase);
@@ -683,14 +692,18 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
         for (int mi = 0; mi < n_mi; ++mi) {
 #pragma unroll
-          for (int pc = 0; pc < AT_PG; ++pc) {
-            const uint32_t sB = sA + a_bytes + pc * b_piece_bytes;
+          for (int pa = 0; pa < PA; ++pa) {
 #pragma unroll
-            for (int k = 0; k < AT_BKT / 16; ++k) {
-              // MN-major: atoms along M/N are one TMA box apart (LBO), 8-row atoms along time 1024 B apart (SBO)
-              const uint64_t ad = make_smem_desc(sA + mi * a_tile_bytes + k * 2048, AT_BOX_BYTES, 1024);
-              const uint64_t bd = make_smem_desc(sB + k * 2048, AT_BOX_BYTES, 1024);
-              mma_f16_ss(tmem_base + (uint32_t)(mi * p.BN), ad, bd, idesc, (tb | pc | k) != 0);
+            for (int pc = 0; pc < AT_PG; ++pc) {
+              if (pa + pc > 1) continue;          // lo*lo is below the kept precision
+              const uint32_t sB = sA + a_bytes + pc * b_piece_bytes;
+#pragma unroll
+              for (int k = 0; k < AT_BKT / 16; ++k) {
+                // MN-major: atoms along M/N are one TMA box apart (LBO), 8-row atoms along time 1024 B apart (SBO)
+                const uint64_t ad = make_smem_desc(sA + (mi * PA + pa) * a_tile_bytes + k * 2048, AT_BOX_BYTES, 1024);
+                const uint64_t bd = make_smem_desc(sB + k * 2048, AT_BOX_BYTES, 1024);
+                mma_f16_ss(tmem_base + (uint32_t)(mi * p.BN), ad, bd, idesc, (tb | pa | pc | k) != 0);
+              }
             }
           }
         }
@@ -731,6 +744,20 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// [T,K] fp32 -> two bf16 pieces [2][T][ld16] (hi + lo = 16 significant bits, fp32 exponent range), zero padded
+__global__ void split_bf16_kernel(int64_t T, int K, const float* __restrict__ src, int64_t lds,
+                                  __nv_bfloat16* __restrict__ dst, int64_t ld16) {
+  const int64_t total = T * ld16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / ld16;
+    const int k = (int)(i - t * ld16);
+    const float v = k < K ? src[(size_t)t * lds + k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[i] = h;
+    dst[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
 }
 
 // posterior [T,K] fp32 -> two fp16 pieces [2][T][ld16] (hi + lo), zero padded
@@ -788,8 +815,36 @@ extern "C" int64_t pmg_atb_f16_workspace_bytes(int64_t T, int K, int N) {
   return (int64_t)splits * K * N * (int64_t)sizeof(float);
 }
 
+extern "C" int pmg_split_bf16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16,
+                              pmg_stream_t stream) {
+  if (T <= 0 || K <= 0 || !src || !dst16 || lds < K || ld16 < K || (ld16 & 7)) return PMG_ERR_BAD_ARG;
+  pmg::split_bf16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(T, K, src, lds, (__nv_bfloat16*)dst16, ld16);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16,
+                             const void* y16_lo, int64_t ldy16, int fmt, float* yw, void* workspace,
+                             int64_t workspace_bytes, pmg_stream_t stream);
+
 extern "C" int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
                            float* yw, void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
+  return atb_pieces_launch(T, K, N, g16, ldg, y16, nullptr, ldy16, 0, yw, workspace, workspace_bytes, stream);
+}
+
+// out[k,n] = sum_t G[t,k] * Y[t,n] with BOTH operands given as two bf16 pieces ([2][T][ld], hi then lo):
+// three tensor-core products (hi*hi + hi*lo + lo*hi), fp32 accumulation, relative error ~2^-16.
+// Same workspace as pmg_atb_f16 (pmg_atb_f16_workspace_bytes).
+extern "C" int pmg_atb_bf16x2(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
+                              float* out, void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
+  if (!y16 || T <= 0) return PMG_ERR_BAD_ARG;
+  const char* lo = (const char*)y16 + (size_t)T * (size_t)ldy16 * 2;
+  return atb_pieces_launch(T, K, N, g16, ldg, y16, lo, ldy16, 1, out, workspace, workspace_bytes, stream);
+}
+
+static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16,
+                             const void* y16_lo, int64_t ldy16, int fmt, float* yw, void* workspace,
+                             int64_t workspace_bytes, pmg_stream_t stream) {
   using namespace pmg;
   if (T <= 0 || K <= 0 || N <= 0 || !g16 || !y16 || !yw) return PMG_ERR_BAD_ARG;
   if (ldg < K || (ldg & 7) || ldy16 < N || (ldy16 & 7)) return PMG_ERR_BAD_ARG;
@@ -799,24 +854,36 @@ extern "C" int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg
   atb_tc_plan(T, K, N, p.BN, p.n_mtiles, p.n_ntiles, p.splits, p.t_per_split);
   if (!workspace || workspace_bytes < (int64_t)p.splits * K * N * (int64_t)sizeof(float)) return PMG_ERR_WORKSPACE;
   p.T = T; p.K = K; p.N = N; p.partial = (float*)workspace;
-  const uint32_t stage_bytes = 4 * AT_BOX_BYTES + AT_PG * (p.BN / 64) * AT_BOX_BYTES;
+  const int PA = y16_lo ? 2 : 1;
+  if (y16_lo && ((uintptr_t)y16_lo & 15)) return PMG_ERR_ALIGNMENT;
+  const uint32_t stage_bytes = 4 * PA * AT_BOX_BYTES + AT_PG * (p.BN / 64) * AT_BOX_BYTES;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.BN);
 
-  CUtensorMap tmY, tmG;
+  CUtensorMap tmY, tmY1, tmG;
   // inner (contiguous) dimension = neurons / latent bins, outer = time; box = 32 time rows x 64 columns
+  // (fp16 and bf16 share the 2-byte tensor-map geometry; the data type only matters to the MMA descriptor)
   int rc = make_tmap_f16(&tmY, y16, (uint64_t)T, (uint64_t)ldy16, (uint64_t)ldy16, AT_BKT);
+  if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+  rc = make_tmap_f16(&tmY1, y16_lo ? y16_lo : y16, (uint64_t)T, (uint64_t)ldy16, (uint64_t)ldy16, AT_BKT);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
   rc = make_tmap_f16(&tmG, g16, (uint64_t)AT_PG * T, (uint64_t)ldg, (uint64_t)ldg, AT_BKT);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   cudaStream_t st = (cudaStream_t)stream;
-  PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p.n_mtiles + 1) / 2, p.n_ntiles, p.splits);
-  atb_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmY, tmG, p);
+  if (PA == 1 && fmt == 0) {
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    atb_tc_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(tmY, tmY1, tmG, p);
+  } else if (PA == 2 && fmt == 1) {
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    atb_tc_kernel<2, 1><<<grid, TC_THREADS, smem, st>>>(tmY, tmY1, tmG, p);
+  } else {
+    return PMG_ERR_BAD_ARG;
+  }
   PMG_LAUNCH_CHECK();
   const int64_t MN = (int64_t)K * N;
   split_reduce_kernel_tc<<<cdiv(MN, 256), 256, 0, st>>>(p.splits, MN, p.partial, yw);

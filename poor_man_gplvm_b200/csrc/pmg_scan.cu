@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
         }
       }
     }
-    if (p.warm_out && t == cr.t_end - c.halo - 1 && cr.s + 1 < c.n_chain) {
+    if (p.warm_out && t == cr.t_end - c.halo - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
       float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -613,8 +613,8 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
         }
       }
     }
-    if (p.warm_out && t == cr.t_begin + c.halo - 1 && cr.s >= 1) {
-      float* o = p.warm_out + (size_t)(cr.s - 1) * 2 * K;
+    if (p.warm_out && t == cr.t_begin + c.halo - 1 && (cr.s >= 1 || !c.left_exact)) {
+      float* o = p.warm_out + ((int64_t)cr.s - 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         if (valid[q]) {
@@ -642,20 +642,36 @@ __global__ void seam_check_kernel(int n, int len, const float* est, int64_t ld_e
   if (i >= n) return;
   const float* a = est + (size_t)i * ld_est;
   const float* b = truth + (size_t)i * ld_truth;
+  __shared__ float sm[2][32];
+  __shared__ float tot[2];
+  // messages are compared up to scale: normalise both to unit sum
+  float sa = 0.f, sb = 0.f;
+  for (int j = threadIdx.x; j < len; j += blockDim.x) { sa += a[j]; sb += b[j]; }
+  sa = warp_sum(sa); sb = warp_sum(sb);
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = sa; sm[1][threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ra = 0.f, rb = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ra += sm[0][w]; rb += sm[1][w]; }
+    tot[0] = ra; tot[1] = rb;
+  }
+  __syncthreads();
+  const float ia = 1.f / tot[0], ib = 1.f / tot[1];
   float e = 0.f;
+  if (!(tot[0] > 0.f) || !(tot[1] > 0.f) || !(ia > 0.f) || !(ib > 0.f)) e = INFINITY;
   for (int j = threadIdx.x; j < len; j += blockDim.x) {
-    const float u = a[j], v = b[j];
+    const float u = a[j] * ia, v = b[j] * ib;
     const float hi = fmaxf(u, v), lo = fminf(u, v);
     if (hi > floor_val) e = fmaxf(e, (hi - lo) / fmaxf(lo, 1e-37f));
     if (!(u == u) || !(v == v)) e = INFINITY;
   }
   e = warp_max(e);
-  __shared__ float sm[32];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[0][threadIdx.x >> 5] = e;
   __syncthreads();
   if (threadIdx.x == 0) {
     float r = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sm[w]);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sm[0][w]);
     err[i] = r;
   }
 }

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = v0[q] * inv_prev; o[K + x0 + q] = v1[q] * inv_prev; }
     }
-    if (p.warm_out && t == cr.t_end - c.halo - 1 && cr.s + 1 < c.n_chain) {
+    if (p.warm_out && t == cr.t_end - c.halo - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
       float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q)
@@ -471,8 +471,8 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = b0[q] * inv; o[K + x0 + q] = b1[q] * inv; }
     }
-    if (p.warm_out && t == cr.t_begin + c.halo - 1 && cr.s >= 1) {
-      float* o = p.warm_out + (size_t)(cr.s - 1) * 2 * K;
+    if (p.warm_out && t == cr.t_begin + c.halo - 1 && (cr.s >= 1 || !c.left_exact)) {
+      float* o = p.warm_out + ((int64_t)cr.s - 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = b0[q] * inv; o[K + x0 + q] = b1[q] * inv; }

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   const int n_steps = (int)(cr.t_end - t0);
   const int i_begin = (int)(cr.t_begin - t0);                    // first bin whose row is stored
   const int e_halo = p.halo_state ? i_begin - 1 : -1;            // warmed-up message in front of the chain
-  const int e_warm = (p.warm_out && cr.s + 1 < c.n_chain) ? (int)(cr.t_end - c.halo - 1 - t0) : -1;
+  const int e_warm = (p.warm_out && (cr.s + 1 < c.n_chain || !c.right_exact)) ? (int)(cr.t_end - c.halo - 1 - t0) : -1;
   const int e_end = p.fwd_end ? n_steps - 1 : -1;
   const int e_first = (p.first_out && cr.t_begin == c.core_begin) ? i_begin : -1;
   int evt = next_event(-1, e_halo, e_warm, e_end, e_first);
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
   const int i_core = (int)(t_hi - (cr.t_end - 1));               // first step of the chain's own bins
   const int e_halo = (p.beta_halo && i_alpha >= 0) ? i_alpha : -1;          // t == t_end
   const int e_end = p.beta_end ? n_steps - 1 : -1;                          // t == t_begin
-  const int e_warm = (p.warm_out && cr.s >= 1) ? (int)(t_hi - (cr.t_begin + c.halo - 1)) : -1;
+  const int e_warm = (p.warm_out && (cr.s >= 1 || !c.left_exact)) ? (int)(t_hi - (cr.t_begin + c.halo - 1)) : -1;
   int evt = next_event(-1, e_halo, e_end, e_warm, -1);
 
   const uint32_t row_bytes = (uint32_t)K * 4;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
     if (i == evt) {                              // rare: seam / warm-start messages (normalised beta)
       if (i == e_halo) store_msg<QP>(p.beta_halo + (size_t)cr.s * 2 * K, b0, inv, b1, inv, x0, K);
       if (i == e_end) store_msg<QP>(p.beta_end + (size_t)cr.s * 2 * K, b0, inv, b1, inv, x0, K);
-      if (i == e_warm) store_msg<QP>(p.warm_out + (size_t)(cr.s - 1) * 2 * K, b0, inv, b1, inv, x0, K);
+      if (i == e_warm) store_msg<QP>(p.warm_out + ((int64_t)cr.s - 1) * 2 * K, b0, inv, b1, inv, x0, K);
       evt = next_event(i, e_halo, e_end, e_warm, -1);
     }
 #pragma unroll

@@ -104,8 +104,11 @@ class EStep:
         # warm-up starts: ping-pong buffers holding, for every chain, the message of the previous pass
         # at the bin where its warm-up starts (forward and backward); before the first pass the forward
         # warm-up starts from the stationary distribution of the prior chain (exact for flat likelihoods)
-        self.fwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
-        self.bwarm = [torch.zeros((S, 2, self.K), **f32), torch.zeros((S, 2, self.K), **f32)]
+        # One extra slot each for the neighbour rank's boundary chain: forward slot c belongs to chain c and slot
+        # S to the right neighbour's first chain; backward slot c+1 belongs to chain c and slot 0 to the left
+        # neighbour's last chain (the kernels see the backward buffers through a view that starts at slot 1).
+        self.fwarm = [torch.zeros((S + 1, 2, self.K), **f32), torch.zeros((S + 1, 2, self.K), **f32)]
+        self.bwarm = [torch.zeros((S + 1, 2, self.K), **f32), torch.zeros((S + 1, 2, self.K), **f32)]
         # entries no local chain ever writes (the warm-up of the first chain starts in the left
         # neighbour's bins, the last chain's backward warm-up in the right neighbour's): keep them at the
         # first-pass defaults — stationary prior for the forward message, all-ones for the backward one
@@ -113,7 +116,7 @@ class EStep:
         for buf in self.fwarm:
             buf[0] = stat if stat is not None else 0.5 / self.K
         for buf in self.bwarm:
-            buf[S - 1] = 1.0
+            buf[S] = 1.0
         self.warm_cur = 0
         self.warm_valid = False
         self.err = torch.zeros(2 * S, **f32)
@@ -141,21 +144,28 @@ class EStep:
         self.em.loglik(tuning, self.ma_latent, 1.0, out=self.ll)
         return self.ll
 
-    def _exchange_fwd(self, compact=False):
+    def _exchange_fwd(self, compact=False, nxt=None):
         """After a forward pass: the last true alpha goes right (seam truth of the neighbour's first
-        chain), the first true alpha goes left (normaliser of the neighbour's last backward seam)."""
+        chain) together with this pass's message at the bin where that chain's next warm-up starts; the first
+        true alpha goes left (normaliser of the neighbour's last backward seam)."""
         if not self.shard.active:
             return
+        K2 = 2 * self.K
         if compact:
             first, last = self.first_out.reshape(-1), self.fwd_end[self.S - 1].reshape(-1)
         else:
             first = self.alpha[self.core.start].reshape(-1)
             last = self.alpha[self.core.stop - 1].reshape(-1)
-        from_left, from_right = self.shard.boundary(first, last)
+        warm = self.fwarm[nxt][self.S].reshape(-1) if nxt is not None else torch.zeros_like(last)
+        from_left, from_right = self.shard.boundary(torch.cat([first, torch.zeros_like(first)]),
+                                                    torch.cat([last, warm]))
         if from_left is not None:
-            self.truth_left = from_left.view(2, self.K)
+            self.truth_left = from_left[:K2].view(2, self.K)
+            w = from_left[K2:]
+            if nxt is not None:
+                self.fwarm[nxt][0].copy_(w.view(2, self.K))
         if from_right is not None:
-            msg = from_right.view(2, self.K)
+            msg = from_right[:K2].view(2, self.K)
             if compact:
                 # row of the compact buffer for the neighbour's first bin: alpha[0,:] and the scalar a1s with
                 # alpha[1,x] = a1s * exp2(s*log2e*(ll[x] - max ll))  (the factor the kernels recompute)
@@ -166,13 +176,19 @@ class EStep:
             else:
                 self.alpha[self.core.stop].copy_(msg)
 
-    def _exchange_bwd(self):
-        """After a backward pass: beta at the first core bin goes left (seam truth of the neighbour's last chain)."""
+    def _exchange_bwd(self, nxt=None):
+        """After a backward pass: beta at the first core bin goes left (seam truth of the neighbour's last
+        chain) together with this pass's message at the bin where that chain's next warm-up starts."""
         if not self.shard.active:
             return
-        _, from_right = self.shard.boundary(self.beta_end[0].reshape(-1), None)
+        K2 = 2 * self.K
+        first = self.beta_end[0].reshape(-1)
+        warm = self.bwarm[nxt][0].reshape(-1) if nxt is not None else torch.zeros_like(first)
+        _, from_right = self.shard.boundary(torch.cat([first, warm]), None)
         if from_right is not None:
-            self.beta_end[self.S].copy_(from_right.view(2, self.K))
+            self.beta_end[self.S].copy_(from_right[:K2].view(2, self.K))
+            if nxt is not None:
+                self.bwarm[nxt][self.S].copy_(from_right[K2:].view(2, self.K))
 
     def _check_fwd(self, compact=False):
         S, K2 = self.S, 2 * self.K
@@ -214,7 +230,8 @@ class EStep:
 
         cur, nxt = self.warm_cur, 1 - self.warm_cur
         f_in = self.fwarm[cur] if self.warm_valid else getattr(self.op, "stationary", None)
-        b_in = self.bwarm[cur] if self.warm_valid else None
+        b_in = self.bwarm[cur][1:] if self.warm_valid else None
+        b_out = self.bwarm[nxt][1:]
 
         def fwd(mode=0, ids=None):
             if compact:
@@ -230,19 +247,19 @@ class EStep:
         def bwd(mode=0, ids=None):
             if compact:
                 ops.backward_compact(self.plan, self.op, self.ll, self.ax, gamma16, beta_halo=self.beta_halo, beta_end=self.beta_end, mode=mode, chain_ids=ids,
-                                     warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=self.bwarm[nxt])
+                                     warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out)
                 return
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
                          mode=mode, chain_ids=ids, gamma16=gamma16,
-                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=self.bwarm[nxt])
+                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out)
 
         fwd()
-        self._exchange_fwd(compact)
+        self._exchange_fwd(compact, nxt)
         self._check_fwd(compact)
         ops.phase("forward")
         bwd()
-        self._exchange_bwd()
+        self._exchange_bwd(nxt)
         self._check_bwd()
         ops.phase("backward")
 
@@ -267,12 +284,12 @@ class EStep:
                     ids = bad.to(device=self.dev, dtype=torch.int32)
                     self.halo_state[ids.long()] = self.truth[ids.long()]      # carry snapshot = new "estimate"
                     fwd(mode=1, ids=ids)
-                self._exchange_fwd(compact)
+                self._exchange_fwd(compact, nxt)
                 self._check_fwd(compact)
                 ef = self._read_err()[self.f_lo:S].clone()
             if redo_bwd:
                 bwd()
-                self._exchange_bwd()
+                self._exchange_bwd(nxt)
                 self._check_bwd()
                 eb = self._read_err()[S:S + self.b_hi].clone()
             for _ in range(S * self.shard.world + 1):
@@ -284,7 +301,7 @@ class EStep:
                     ids = bad.to(device=self.dev, dtype=torch.int32)
                     self.beta_halo[ids.long()] = self.beta_end[ids.long() + 1]
                     bwd(mode=1, ids=ids)
-                self._exchange_bwd()
+                self._exchange_bwd(nxt)
                 self._check_bwd()
                 eb = self._read_err()[S:S + self.b_hi].clone()
             self.warm_cur, self.warm_valid = nxt, True

@@ -478,6 +478,41 @@ def atb_f16(g16, y16, K, out=None):
     return out
 
 
+def split_bf16(src):
+    """fp32 [T,K] (row stride >= K) -> bf16 hi/lo pieces [2,T,ld], ld = K rounded up to 8."""
+    lib = _lib.load()
+    if src.dim() != 2 or src.dtype != torch.float32 or not src.is_cuda or src.stride(1) != 1:
+        raise TypeError("split_bf16 expects a float32 CUDA matrix with unit inner stride")
+    T, K = src.shape
+    ld = (K + 7) // 8 * 8
+    out = (torch.zeros if ld != K else torch.empty)((2, T, ld), dtype=torch.bfloat16, device=src.device)
+    check(lib.pmg_split_bf16(T, K, _p(src), src.stride(0), _p(out), ld, _stream()), "pmg_split_bf16")
+    _count(1)
+    return out
+
+
+XI_TC_MIN_BINS = int(os.environ.get("PMG_XI_TC_MIN_BINS", "4096"))
+
+
+def atb_bf16x2(A, B, out=None):
+    """C[M,N] = sum_t A[t,:M]^T B[t,:N] on the tensor cores: both operands as two bf16 pieces, three products
+    (relative error ~2^-16 per term, fp32 accumulation).  The transition-count GEMM of decode_latent."""
+    lib = _lib.load()
+    if A.dim() != 2 or B.dim() != 2 or A.shape[0] != B.shape[0]:
+        raise ValueError("atb expects [T,M] and [T,N]")
+    T, M = A.shape
+    N = B.shape[1]
+    a16, b16 = split_bf16(A), split_bf16(B)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    nbytes = lib.pmg_atb_f16_workspace_bytes(T, M, N)
+    ws = _workspace(nbytes, A.device)
+    check(lib.pmg_atb_bf16x2(T, M, N, _p(a16), a16.shape[2], _p(b16), b16.shape[2], _p(out), _p(ws), ws.numel(),
+                             _stream()), "pmg_atb_bf16x2")
+    _count(2)
+    return out
+
+
 def xi_finalize(G, logP, logM_host):
     lib = _lib.load()
     _f32(G, "G", 2); _f32(logP, "logP", 3)

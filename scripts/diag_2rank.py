@@ -1,0 +1,31 @@
+"""Per-iteration seam statistics of the time-sharded EM loop (torchrun --nproc-per-node 2)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import poor_man_gplvm_b200 as pmg
+from poor_man_gplvm_b200.core import EMLoop
+from poor_man_gplvm_b200.shard import TimeShard
+from poor_man_gplvm_b200.synthetic import make_dataset_torch
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+T, N, K = int(os.environ.get("T", 1000000)), 500, 400
+y = make_dataset_torch(T, N, K, dev, seed=1234 + rank)["y"].to(torch.float32).contiguous()
+model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=10.0, movement_variance=1.0, device=dev)
+model.params = np.random.default_rng(1).standard_normal((model.n_basis, N)).astype(np.float32)
+P, logP, M, logM, op = model._transition_pack({})
+ma_n, ma_l = model._masks(None, None, T)
+g = torch.Generator(device=dev); g.manual_seed(99)
+post0 = torch.rand((T, K), generator=g, device=dev)
+lp0 = torch.log(post0 / post0.sum(dim=1, keepdim=True)); del post0
+loop = EMLoop(model, y, op, ma_n, ma_l, 1.0, model.tuning_basis, lp0, model.param_prior_std, 0.01, 1000, 1e-6, shard=TimeShard())
+es = loop.es
+for i in range(int(os.environ.get("ITERS", 10))):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res, m = loop.iteration()
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) * 1e3
+    err = es.err_host.clone()
+    ef, eb = err[es.f_lo:es.S], err[es.S:es.S + es.b_hi]
+    print("rank %d it %d: %.1f ms relay f %d b %d | final seam err f max %.2e (arg %d) b max %.2e (arg %d) | S=%d f_lo=%d b_hi=%d" %
+          (rank, i, dt, res.n_relay_fwd, res.n_relay_bwd, float(ef.max()), int(ef.argmax()), float(eb.max()), int(eb.argmax()), es.S, es.f_lo, es.b_hi), flush=True)
+dist.destroy_process_group()

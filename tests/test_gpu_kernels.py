@@ -259,6 +259,41 @@ def test_atb_matches_numpy(ops, T, M, N, impl):
     assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 5e-6
 
 
+@pytest.mark.parametrize("T,M,N", [(1, 3, 5), (1000, 96, 40), (4099, 130, 70), (6001, 800, 800), (3000, 264, 520)])
+def test_atb_bf16x2_tensor_core_matches_numpy(ops, T, M, N):
+    """Transition-count GEMM on tcgen05: both operands as bf16 hi/lo pieces, three products.  Entries
+    span many orders of magnitude (filtered posteriors); every term keeps 16 significant bits at any scale."""
+    rng = np.random.default_rng(T + M)
+    A = (rng.random((T, M)) ** 8 * 10.0 ** rng.integers(-12, 1, size=(T, M))).astype(np.float32)
+    B = (rng.random((T, N)) ** 8 * 10.0 ** rng.integers(-12, 3, size=(T, N))).astype(np.float32)
+    want = A.astype(np.float64).T @ B.astype(np.float64)
+    # row-offset views, as core._transition_counts passes them
+    Ad, Bd = dev(np.concatenate([A[:1], A])), dev(np.concatenate([B, B[:1]]))
+    got = host(ops.atb_bf16x2(Ad[1:], Bd[:-1]))
+    assert got.shape == (M, N)
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)) < 6e-5
+    # tiny inputs are not flushed: scale everything down by 1e-20
+    got_s = host(ops.atb_bf16x2(dev(A * np.float32(1e-10)), dev(B * np.float32(1e-10))))
+    assert np.max(np.abs(got_s - want * 1e-20) / np.maximum(np.abs(want * 1e-20), 1e-36)) < 6e-5
+
+
+def test_seam_check_is_scale_invariant(ops):
+    """Messages are defined up to a positive factor (both passes renormalise every step): the seam check compares
+    them after normalisation, so a rescaled copy passes and a perturbed entry is reported with its relative size."""
+    rng = np.random.default_rng(3)
+    a = (rng.random((5, 64)) ** 4).astype(np.float32)
+    b = a * np.array([1.0, 3.7, 1e-3, 2.0, 1.0], np.float32)[:, None]
+    b[3, 10] *= 1.01
+    b[4, :] = 0.0
+    ad, bd = dev(a), dev(b)
+    err = torch.zeros(5, device="cuda")
+    ops.seam_check(5, 64, ad.data_ptr(), 64, bd.data_ptr(), 64, err)
+    e = host(err)
+    assert np.all(e[:3] < 1e-6)
+    assert 5e-3 < e[3] < 2e-2
+    assert not np.isfinite(e[4])
+
+
 @pytest.mark.parametrize("T,K,N", [(1, 3, 5), (1000, 100, 30), (4099, 130, 70), (20000, 400, 500), (3000, 600, 200)])
 def test_atb_f16_tensor_core_matches_numpy(ops, T, K, N):
     """Statistics GEMM on tcgen05: posterior as fp16 hi/lo pieces (22 bits), counts exact in fp16."""
