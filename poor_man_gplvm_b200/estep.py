@@ -121,6 +121,7 @@ class EStep:
         self.warm_valid = False
         self.err = torch.zeros(2 * S, **f32)
         self.err_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
+        self._gmax_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         # rows of alpha holding the true message in front of chain c (c >= 1): bin t_begin(c) - 1
         self.rows_f = self.core.start + torch.arange(1, S, device=self.dev) * self.chunk_len - 1
         # which seams exist: forward seam c sits in front of chain c; backward seam c behind chain c
@@ -156,7 +157,20 @@ class EStep:
         else:
             first = self.alpha[self.core.start].reshape(-1)
             last = self.alpha[self.core.stop - 1].reshape(-1)
-        warm = self.fwarm[nxt][self.S].reshape(-1) if nxt is not None else torch.zeros_like(last)
+        # message at the bin in front of the right neighbour's first warm-up bin.  The kernels' slot S holds it
+        # only when that bin lies in the last chain's own range; with a ragged (short) last chunk it lies in an
+        # earlier chain, so it is read back from the stored filtered posterior instead.
+        t_star = self.core.stop - self.halo - 1
+        if nxt is None:
+            warm = torch.zeros_like(last)
+        elif t_star < self.core.start:
+            warm = self.fwarm[nxt][self.S].reshape(-1)
+        elif compact:
+            row = self.ll[t_star]
+            E = torch.exp2((row - row.max()) * (self.scale * 1.4426950408889634))
+            warm = torch.cat([self.ax[t_star, :self.K], self.ax[t_star, self.K] * E])
+        else:
+            warm = self.alpha[t_star].reshape(-1)
         from_left, from_right = self.shard.boundary(torch.cat([first, torch.zeros_like(first)]),
                                                     torch.cat([last, warm]))
         if from_left is not None:
@@ -213,6 +227,24 @@ class EStep:
         torch.cuda.current_stream().synchronize()
         return self.err_host
 
+    def _read_err_global(self):
+        """Seam errors of this rank plus, for time-sharded runs, whether ANY rank has a failing forward /
+        backward seam -- one collective and one synchronisation for the common case of no repair at all."""
+        if not self.shard.active:
+            err = self._read_err()
+            ef, eb = err[self.f_lo:self.S], err[self.S:self.S + self.b_hi]
+            return err, bool(ef.numel() and float(ef.max()) > self.seam_tol), \
+                bool(eb.numel() and float(eb.max()) > self.seam_tol)
+        S = self.S
+        zero = self.err.new_zeros(())
+        m = torch.stack([self.err[self.f_lo:S].max() if S > self.f_lo else zero,
+                         self.err[S:S + self.b_hi].max() if self.b_hi > 0 else zero])
+        m = torch.nan_to_num(m, nan=float("inf"))
+        self.shard.allreduce_max_(m)
+        self._gmax_host.copy_(m, non_blocking=True)
+        err = self._read_err()
+        return err, bool(self._gmax_host[0] > self.seam_tol), bool(self._gmax_host[1] > self.seam_tol)
+
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
         the hi/lo pieces of the latent posterior."""
@@ -266,7 +298,7 @@ class EStep:
         n_relay_f = n_relay_b = 0
         ef = eb = torch.zeros(0)
         if S > 1 or self.shard.active:
-            err = self._read_err()
+            err, any_f, any_b = self._read_err_global()
             ef = err[self.f_lo:S].clone()         # ef[i]: seam in front of chain f_lo + i
             eb = err[S:S + self.b_hi].clone()     # eb[c]: seam behind chain c
             # Seam repair = parallel (Jacobi) sweeps: every chain whose incoming message was off restarts,
@@ -274,7 +306,7 @@ class EStep:
             # seams are then re-verified against the messages those restarts produced.  Each sweep extends
             # the effective warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length.
             redo_bwd = False
-            for _ in range(S * self.shard.world + 1):
+            for _ in range(S * self.shard.world + 1 if any_f else 0):
                 bad = torch.nonzero(ef > self.seam_tol).flatten() + self.f_lo
                 if self.shard.max_int(bad.numel(), self.dev) == 0:
                     break
@@ -292,7 +324,7 @@ class EStep:
                 self._exchange_bwd(nxt)
                 self._check_bwd()
                 eb = self._read_err()[S:S + self.b_hi].clone()
-            for _ in range(S * self.shard.world + 1):
+            for _ in range(S * self.shard.world + 1 if (any_b or redo_bwd) else 0):
                 bad = torch.nonzero(eb > self.seam_tol).flatten()
                 if self.shard.max_int(bad.numel(), self.dev) == 0:
                     break

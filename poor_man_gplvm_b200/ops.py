@@ -403,7 +403,10 @@ def backward_compact(plan, op, ll, ax, gamma16, beta_halo=None, beta_end=None, b
     _count(1)
 
 
-def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1e-20):
+def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1e-12):
+    """err[i] = max relative difference of the unit-sum-normalised messages over entries > floor_val.  Entries
+    below 1e-12 of a normalised message cannot reach 1e-7 in any posterior (every state is entered by a jump with
+    probability >= p_move_to_jump/K per bin, which bounds the ratio of backward-message entries)."""
     lib = _lib.load()
     check(lib.pmg_seam_check(int(n), int(length), C.c_void_p(est_ptr), int(ld_est), C.c_void_p(truth_ptr),
                              int(ld_truth), float(floor_val), _p(err), _stream()), "pmg_seam_check")

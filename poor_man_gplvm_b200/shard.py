@@ -99,6 +99,11 @@ class TimeShard:
             t.copy_(flat[o:o + n].reshape(t.shape).to(t.dtype))
             o += n
 
+    def allreduce_max_(self, t):
+        """In-place element-wise maximum over ranks."""
+        if self.active:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
     def max_int(self, v, device):
         if not self.active:
             return int(v)

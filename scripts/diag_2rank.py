@@ -20,6 +20,23 @@ post0 = torch.rand((T, K), generator=g, device=dev)
 lp0 = torch.log(post0 / post0.sum(dim=1, keepdim=True)); del post0
 loop = EMLoop(model, y, op, ma_n, ma_l, 1.0, model.tuning_basis, lp0, model.param_prior_std, 0.01, 1000, 1e-6, shard=TimeShard())
 es = loop.es
+_orig_check = es._check_fwd
+state = {"n": 0}
+def check_fwd(compact=False):
+    _orig_check(compact)
+    if rank == 1 and state["n"] < 40 and os.environ.get("DBG"):
+        state["n"] += 1
+        torch.cuda.synchronize()
+        a = es.halo_state[0].reshape(-1).double(); b = es.truth[0].reshape(-1).double()
+        a = a / a.sum(); b = b / b.sum()
+        rel = (a - b).abs() / torch.maximum(torch.minimum(a, b), torch.tensor(1e-37, device=a.device, dtype=a.dtype))
+        rel = torch.where(torch.maximum(a, b) > 1e-20, rel, torch.zeros_like(rel))
+        j = int(rel.argmax())
+        big = (torch.maximum(a, b) > 1e-6)
+        print("  [rank1 chain0 check %d] err %.3e at j=%d (a=%.3e b=%.3e) | max rel err over entries>1e-6: %.3e | err[0]=%.3e sum_a1=%.4f sum_b1=%.4f" %
+              (state["n"], float(rel.max()), j, float(a[j]), float(b[j]), float(rel[big].max()) if big.any() else 0.0, float(es.err[0]),
+               float(a[es.K:].sum()), float(b[es.K:].sum())), flush=True)
+es._check_fwd = check_fwd
 for i in range(int(os.environ.get("ITERS", 10))):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res, m = loop.iteration()
