@@ -133,7 +133,9 @@ class EMLoop:
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
         self._n_mstep = 0
         self._hist = self._new_hist_block()
-        self._tuning = torch.empty((self.Phi.shape[0], model.n_neuron), dtype=torch.float32, device=self.W.device)
+        self._tuning = torch.empty((2, self.Phi.shape[0], model.n_neuron), dtype=torch.float32, device=self.W.device)
+        self._tuning_i = 0
+        self._spec = None                  # M-step result enqueued ahead for the next iteration (see iteration)
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
         self.use_tc = self.es.y16 is not None and self.es.y16.exact
         T_core, K = y_dev.shape[0], op.K
@@ -163,23 +165,23 @@ class EMLoop:
         """Output buffers of the next M-step.  Nothing that outlives an iteration is allocated per iteration:
         a device allocation that misses the caching allocator is a driver call behind the process's memory-map
         lock, which fit_em's background page-population of the host result buffers holds most of the time
-        (measured: sporadic 40-180 ms stalls of single EM iterations).  The tuning buffer is reused every
-        iteration; the Adam histories live in blocks of _HIST_BLOCK iterations."""
+        (measured: sporadic 40-180 ms stalls of single EM iterations).  Two tuning buffers alternate; the Adam
+        histories live in blocks of _HIST_BLOCK iterations."""
         slot = self._n_mstep % self._HIST_BLOCK
         if slot == 0 and self._n_mstep > 0:
             self._hist = self._new_hist_block()
         self._n_mstep += 1
         lh, eh, ni, fin = self._hist
-        return lh[slot], eh[slot], ni[slot:slot + 1], fin[slot], self._tuning
+        self._tuning_i ^= 1
+        return lh[slot], eh[slot], ni[slot:slot + 1], fin[slot], self._tuning[self._tuning_i]
 
     def _new_hist_block(self):
         dev, n, mi = self.W.device, self._HIST_BLOCK, int(self.maxiter)
         return (torch.empty((n, mi), dtype=torch.float32, device=dev), torch.empty((n, mi), dtype=torch.float32, device=dev),
                 torch.empty(n, dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.float32, device=dev))
 
-    def iteration(self, want_gamma=False, want_dyn=False, want_gamma_lat=False):
-        """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path).
-        The returned tuning (m_res[4]) is a buffer that the next iteration overwrites."""
+    def _stats_and_mstep(self):
+        """Sufficient statistics of the current posterior + the Adam M-step (reference core.py:807-810)."""
         if self.use_tc:
             # reference core.py:807; the ones column of the fp16 counts makes column N = sum_t gamma
             stats = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)
@@ -192,8 +194,39 @@ class EMLoop:
         m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
                                self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
         ops.phase("mstep")
+        return m_res
+
+    def iteration(self, want_gamma=False, want_dyn=False, want_gamma_lat=False, speculate=False):
+        """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path).
+        The returned tuning (m_res[4]) is one of two buffers; the iteration after the next overwrites it.
+
+        speculate=True: the statistics GEMM and the M-step of the NEXT iteration are enqueued right behind this
+        iteration's backward pass, before the launching thread waits for the seam verdict, so the GPU has work
+        while the host synchronises (the one synchronisation per EM iteration).  They only read what the
+        backward pass wrote; if a seam then fails and chains are re-run, the Adam state is restored from a
+        snapshot and the next iteration recomputes them.  Pass False for the last iteration of a fit."""
+        spec_ok = bool(speculate and self.use_tc)
+        if self._spec is not None:
+            m_res, self._spec = self._spec, None
+        else:
+            m_res = self._stats_and_mstep()
+        nxt = {}
+
+        def enqueue_next():
+            st = self.state
+            nxt["snap"] = (self.W.clone(), st.mu.clone(), st.nu.clone(), st.count.clone(), self._n_mstep,
+                           self._hist, self._tuning_i)
+            nxt["m_res"] = self._stats_and_mstep()
+
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
-                          want_dyn=want_dyn, want_r=False, gamma16=self.gamma16)
+                          want_dyn=want_dyn, want_r=False, gamma16=self.gamma16,
+                          before_sync=enqueue_next if spec_ok else None)
+        if "m_res" in nxt:
+            if res.repaired:
+                W, mu, nu, count, self._n_mstep, self._hist, self._tuning_i = nxt["snap"]
+                self.W.copy_(W); self.state.mu.copy_(mu); self.state.nu.copy_(nu); self.state.count.copy_(count)
+            else:
+                self._spec = nxt["m_res"]
         self.gamma_lat = res.gamma_lat                             # reference core.py:668
         if res.tw is not None:
             self.tw = res.tw
@@ -541,7 +574,8 @@ class PoissonGPLVMJump1D:
             tm.iteration()
             last = i == n_iter - 1
             snap = (i % save_every == 0)
-            res, m_res = loop.iteration(want_gamma=(last or snap), want_dyn=last, want_gamma_lat=last)
+            res, m_res = loop.iteration(want_gamma=(last or snap), want_dyn=last, want_gamma_lat=last,
+                                        speculate=not last)
             m_hist.append(m_res)
             tuning = m_res[4]
             lml_dev.append(res.log_marginal)

@@ -41,7 +41,8 @@ def plan_chunks(n_core, halo, sm_count, chains_per_sm=8):
 class EStepResult:
     """Tensors cover this rank's core bins only (views into the E-step buffers)."""
     __slots__ = ("ll", "alpha", "lmr", "gamma", "gamma_lat", "dyn_marg", "r", "tw", "log_marginal",
-                 "n_relay_fwd", "n_relay_bwd", "seam_err_fwd", "seam_err_bwd", "plan", "alpha_ext", "r_ext", "core")
+                 "n_relay_fwd", "n_relay_bwd", "seam_err_fwd", "seam_err_bwd", "plan", "alpha_ext", "r_ext", "core",
+                 "repaired")
 
 
 class EStep:
@@ -245,9 +246,13 @@ class EStep:
         err = self._read_err()
         return err, bool(self._gmax_host[0] > self.seam_tol), bool(self._gmax_host[1] > self.seam_tol)
 
-    def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None):
+    def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
+            before_sync=None):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
-        the hi/lo pieces of the latent posterior."""
+        the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes and
+        the seam checks are enqueued, before the launching thread waits for the verdict (work enqueued there
+        keeps the GPU busy during the synchronisation; ``res.repaired`` tells whether chains were re-run after
+        it, i.e. whether what it read from this E-step's outputs was final)."""
         S, K = self.S, self.K
         f32 = dict(dtype=torch.float32, device=self.dev)
         # EM fast path: only the fp16 posterior pieces and sum_t gamma are wanted -> compact kernels
@@ -297,6 +302,9 @@ class EStep:
 
         n_relay_f = n_relay_b = 0
         ef = eb = torch.zeros(0)
+        any_f = any_b = False
+        if before_sync is not None:
+            before_sync()
         if S > 1 or self.shard.active:
             err, any_f, any_b = self._read_err_global()
             ef = err[self.f_lo:S].clone()         # ef[i]: seam in front of chain f_lo + i
@@ -354,6 +362,7 @@ class EStep:
         res.tw = None if compact else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
         res.log_marginal = lmr[c].sum(dtype=torch.float64)
         res.n_relay_fwd, res.n_relay_bwd = n_relay_f, n_relay_b
+        res.repaired = bool(any_f or any_b)                   # same verdict on every rank
         res.seam_err_fwd = float(ef.max()) if ef.numel() else 0.0
         res.seam_err_bwd = float(eb.max()) if eb.numel() else 0.0
         res.plan = self.plan
