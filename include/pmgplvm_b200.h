@@ -73,6 +73,14 @@ int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, c
  *      Kpad = ceil(K / BN) * BN with BN = pmg_emission_tile_n(K); padding rows/columns are zero. */
 int pmg_counts_to_f16(int64_t T, int N, const float* y, int64_t ldy, void* y16, int64_t ld16,
                       int* inexact_count, pmg_stream_t stream);
+
+/* The two passes above fused (one read of the counts): fp16 copy [T, ld16] with an optional column of ones at
+ * index N (ones_col; the statistics GEMM then also returns sum_t gamma) and zero padding up to ld16, the exactness
+ * counter, lgam[t] = sum_n m_n lgamma(y[t,n]+1) (reference decoder.py:40) and optionally ysum[t] = sum_n m_n y[t,n].
+ * ma_neuron: NULL or a vector [N]. */
+int pmg_counts_prepare(int64_t T, int N, const float* y, int64_t ldy, const float* ma_neuron, void* y16,
+                       int64_t ld16, int ones_col, int* inexact_count, float* lgam, float* ysum,
+                       pmg_stream_t stream);
 int pmg_emission_tile_n(int K);
 int pmg_emission_prepare_f16(int K, int N, const float* tuning, const float* ma_neuron, float dt, int Kpad,
                              int64_t ld16, void* loglam16, float* lam_sum, pmg_stream_t stream);

@@ -47,6 +47,88 @@ __global__ void counts_to_f16_kernel(int64_t T, int N, const float* __restrict__
   }
 }
 
+// One pass over the spike counts for everything an E-step needs from them (reference decoder.py:40: the
+// gammaln(y+1) term depends on y only): fp16 copy [T, ld16] (+ optional column of ones at index N, zero padding),
+// exactness flag, lgam[t] = sum_n m_n lgamma(y[t,n]+1) and optionally ysum[t] = sum_n m_n y[t,n].
+// One warp per time bin; VEC: rows are 16-byte aligned and N % 4 == 0 (float4 loads, 8-byte stores).
+__device__ __forceinline__ float lgamma1p_count(float v) {
+  // log(n!) for the small integer counts that make up spike data; anything else through lgammaf
+  if (v == 0.f || v == 1.f) return 0.f;
+  if (v == 2.f) return 0.69314718055994531f;
+  if (v == 3.f) return 1.7917594692280550f;
+  if (v == 4.f) return 3.1780538303479458f;
+  if (v == 5.f) return 4.7874917427820458f;
+  if (v == 6.f) return 6.5792512120101012f;
+  return lgammaf(v + 1.f);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+counts_prepare_kernel(int64_t T, int N, const float* __restrict__ y, int64_t ldy, const float* __restrict__ ma,
+                      __half* __restrict__ y16, int64_t ld16, int ones_col, int* __restrict__ inexact,
+                      float* __restrict__ lgam, float* __restrict__ ysum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float* row = y + (size_t)t * ldy;
+  __half* orow = y16 + (size_t)t * ld16;
+  float acc = 0.f, ys = 0.f;
+  int bad = 0;
+  if (VEC) {
+    const int n4 = N >> 2;
+    for (int j0 = 0; j0 < n4; j0 += 128) {         // four independent 16-byte loads per lane in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 32 + lane;
+        v[u] = j < n4 ? __ldcs(reinterpret_cast<const float4*>(row) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 32 + lane;
+        if (j >= n4) continue;
+        const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float m[4] = {1.f, 1.f, 1.f, 1.f};
+        if (ma) {
+          const float4 m4 = __ldg(reinterpret_cast<const float4*>(ma) + j);
+          m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+        }
+        __half h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __float2half_rn(x[e]);
+          bad |= (__half2float(h[e]) != x[e]);
+          acc = fmaf(m[e], lgamma1p_count(x[e]), acc);
+          ys = fmaf(m[e], x[e], ys);
+        }
+        uint2 pk;
+        pk.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        pk.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        reinterpret_cast<uint2*>(orow)[j] = pk;
+      }
+    }
+  } else {
+    for (int n = lane; n < N; n += 32) {
+      const float x = row[n];
+      const float m = ma ? ma[n] : 1.f;
+      const __half h = __float2half_rn(x);
+      bad |= (__half2float(h) != x);
+      acc = fmaf(m, lgamma1p_count(x), acc);
+      ys = fmaf(m, x, ys);
+      orow[n] = h;
+    }
+  }
+  for (int n = N + lane; n < (int)ld16; n += 32)
+    orow[n] = (ones_col && n == N) ? __float2half_rn(1.f) : __float2half_rn(0.f);
+  acc = warp_sum(acc);
+  ys = warp_sum(ys);
+  if (lane == 0) {
+    lgam[t] = acc;
+    if (ysum) ysum[t] = ys;
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(inexact, 1);
+}
+
 // loglam pieces [2][Kpad][ld16]; rows >= K and columns >= N are zero.  One CTA per padded row.
 __global__ void emission_prepare_f16_kernel(int K, int N, const float* __restrict__ tuning,
                                             const float* __restrict__ ma_neuron, float dt, int Kpad, int64_t ld16,
@@ -489,6 +571,25 @@ extern "C" int pmg_counts_to_f16(int64_t T, int N, const float* y, int64_t ldy, 
   cudaStream_t st = (cudaStream_t)stream;
   PMG_CUDA_CHECK(cudaMemsetAsync(inexact_count, 0, sizeof(int), st));
   pmg::counts_to_f16_kernel<<<148 * 8, 256, 0, st>>>(T, N, y, ldy, (__half*)y16, ld16, inexact_count);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_counts_prepare(int64_t T, int N, const float* y, int64_t ldy, const float* ma_neuron, void* y16,
+                                  int64_t ld16, int ones_col, int* inexact_count, float* lgam, float* ysum,
+                                  pmg_stream_t stream) {
+  if (T <= 0 || N <= 0 || !y || !y16 || !inexact_count || !lgam || ldy < N || (ld16 & 7)) return PMG_ERR_BAD_ARG;
+  if (ld16 < N + (ones_col ? 1 : 0)) return PMG_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PMG_CUDA_CHECK(cudaMemsetAsync(inexact_count, 0, sizeof(int), st));
+  const bool vec = (N & 3) == 0 && (ldy & 3) == 0 && ((uintptr_t)y & 15) == 0 && (!ma_neuron || ((uintptr_t)ma_neuron & 15) == 0);
+  const unsigned grid = (unsigned)pmg::cdiv(T, 8);
+  if (vec)
+    pmg::counts_prepare_kernel<true><<<grid, 256, 0, st>>>(T, N, y, ldy, ma_neuron, (__half*)y16, ld16, ones_col,
+                                                           inexact_count, lgam, ysum);
+  else
+    pmg::counts_prepare_kernel<false><<<grid, 256, 0, st>>>(T, N, y, ldy, ma_neuron, (__half*)y16, ld16, ones_col,
+                                                            inexact_count, lgam, ysum);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

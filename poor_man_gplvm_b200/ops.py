@@ -109,10 +109,12 @@ def emission_poisson(y, loglam, lam_sum, lgam, ma_latent=None, out=None):
 class CountsF16:
     """fp16 copy of the spike counts for the tensor-core kernels ([T, ld16], zero padded)."""
 
-    def __init__(self, y, ones_col=False):
+    def __init__(self, y, ones_col=False, ma_vec=None, want_lgam=False, want_ysum=False):
         """ones_col: append a column of ones (index N) so that the statistics GEMM also returns sum_t gamma
         (reference fit_tuning_helper.py:41) as column N of its output; the emission GEMM multiplies it by the
-        zero padding of its right-hand operand."""
+        zero padding of its right-hand operand.
+        want_lgam: the same pass over the counts also produces ``self.lgam`` [T] = sum_n m_n lgamma(y+1)
+        (and ``self.ysum`` with want_ysum) for the neuron mask vector ``ma_vec`` (None = all ones)."""
         lib = _lib.load()
         _f32(y, "y", 2)
         self.T, self.N = y.shape
@@ -121,11 +123,24 @@ class CountsF16:
         self.ld = (self.N + (1 if ones_col else 0) + al - 1) // al * al
         self.data = torch.empty((self.T, self.ld), dtype=torch.float16, device=y.device)
         self._inexact = torch.zeros(1, dtype=torch.int32, device=y.device)
-        check(lib.pmg_counts_to_f16(self.T, self.N, _p(y), self.N, _p(self.data), self.ld, _p(self._inexact),
-                                    _stream()), "pmg_counts_to_f16")
-        _count(1)
-        if ones_col:
-            self.data[:, self.N] = 1.0
+        self.lgam = self.ysum = None
+        if want_lgam:
+            if ma_vec is not None:
+                _f32(ma_vec, "ma_neuron", 1)
+                if ma_vec.shape[0] != self.N:
+                    raise ValueError("ma_neuron must be [N]")
+            self.lgam = torch.empty(self.T, dtype=torch.float32, device=y.device)
+            self.ysum = torch.empty(self.T, dtype=torch.float32, device=y.device) if want_ysum else None
+            check(lib.pmg_counts_prepare(self.T, self.N, _p(y), y.stride(0), _p(ma_vec), _p(self.data), self.ld,
+                                         int(self.ones_col), _p(self._inexact), _p(self.lgam), _p(self.ysum),
+                                         _stream()), "pmg_counts_prepare")
+            _count(1)
+        else:
+            check(lib.pmg_counts_to_f16(self.T, self.N, _p(y), self.N, _p(self.data), self.ld, _p(self._inexact),
+                                        _stream()), "pmg_counts_to_f16")
+            _count(1)
+            if ones_col:
+                self.data[:, self.N] = 1.0
         self._exact = None
 
     @property
@@ -232,6 +247,11 @@ class EmissionOperands:
         else:
             self.ma_vec = ma_neuron
             self.A = y
+            if impl == 0:
+                # one pass over the counts: fp16 copy, exactness flag and the lgamma row term
+                self.A16 = CountsF16(y, ones_col=ones_col, ma_vec=ma_neuron, want_lgam=True)
+                self.lgam = self.A16.lgam
+                return
             self.lgam = lgamma_rowsum(y, ma_neuron)
         # per-bin dt is not fp16-exact: that path always runs on the fp32 tiles
         self.A16 = (CountsF16(self.A, ones_col=(ones_col and self.mode == 0))

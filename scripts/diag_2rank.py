@@ -37,6 +37,28 @@ def check_fwd(compact=False):
               (state["n"], float(rel.max()), j, float(a[j]), float(b[j]), float(rel[big].max()) if big.any() else 0.0, float(es.err[0]),
                float(a[es.K:].sum()), float(b[es.K:].sum())), flush=True)
 es._check_fwd = check_fwd
+from poor_man_gplvm_b200 import ops as _ops
+marks = []
+if os.environ.get("HOSTMARKS"):
+    _ops.PHASE_HOOK = lambda name: marks.append((name, time.perf_counter()))
+    _o = es._read_err_global
+    def _r():
+        marks.append(("enqueued", time.perf_counter())); out = _o(); marks.append(("verdict", time.perf_counter())); return out
+    es._read_err_global = _r
+    for k in range(12):
+        loop.iteration(speculate=True)
+    torch.cuda.synchronize(); dist.barrier(); marks.clear()
+    t_begin = time.perf_counter()
+    for k in range(8):
+        marks.append(("begin", time.perf_counter())); loop.iteration(speculate=True)
+    torch.cuda.synchronize(); t_end = time.perf_counter()
+    if rank == 0:
+        print("free-running: %.3f ms/iter" % ((t_end - t_begin) * 1e3 / 8))
+        acc = {}
+        for (n0, t0), (n1, t1) in zip(marks[:-1], marks[1:]):
+            acc[n1] = acc.get(n1, 0.0) + (t1 - t0) * 1e3 / 8
+        print("host ms per iteration by segment (time up to the mark):", {k: round(v, 3) for k, v in acc.items()})
+    dist.destroy_process_group(); sys.exit(0)
 for i in range(int(os.environ.get("ITERS", 10))):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res, m = loop.iteration()

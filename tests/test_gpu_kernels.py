@@ -68,6 +68,34 @@ def test_emission_noninteger_and_large_counts(ops):
     assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 3e-6
 
 
+@pytest.mark.parametrize("T,N,ones", [(1, 5, True), (257, 500, True), (1000, 37, False), (513, 128, True)])
+def test_counts_prepare_matches_separate_passes(ops, T, N, ones):
+    """Fused pass over the counts (fp16 copy + ones column + exactness + lgamma row term, decoder.py:40) against
+    the two-kernel path and NumPy/SciPy."""
+    from scipy.special import gammaln
+    rng = np.random.default_rng(T + N)
+    y = rng.poisson(1.3, size=(T, N)).astype(np.float32)
+    y[rng.random((T, N)) < 0.01] = 40.0            # a few large counts (beyond the small-count table)
+    ma = (rng.random(N) > 0.2).astype(np.float32)
+    for mask in (None, ma):
+        c = ops.CountsF16(dev(y), ones_col=ones, ma_vec=None if mask is None else dev(mask), want_lgam=True,
+                          want_ysum=True)
+        assert c.exact
+        got = host(c.data.float())
+        assert np.array_equal(got[:, :N], y)
+        if ones:
+            assert np.all(got[:, N] == 1.0)
+        assert np.all(got[:, N + (1 if ones else 0):] == 0.0)
+        w = np.ones(N) if mask is None else mask.astype(np.float64)
+        want = (gammaln(y.astype(np.float64) + 1.0) * w).sum(axis=1)
+        assert np.max(np.abs(host(c.lgam) - want) / np.maximum(1.0, np.abs(want))) < 2e-6
+        assert np.allclose(host(c.ysum), (y * w).sum(axis=1), rtol=1e-6)
+        ref = host(ops.lgamma_rowsum(dev(y), None if mask is None else dev(mask)))
+        assert np.max(np.abs(host(c.lgam) - ref) / np.maximum(1.0, np.abs(ref))) < 2e-6
+    y2 = y.copy(); y2[T // 2, N // 2] = 0.3          # not representable exactly as a count
+    assert not ops.CountsF16(dev(y2), ones_col=ones, want_lgam=True).exact
+
+
 def test_naive_bayes_normalize(ops):
     d = make_dataset(700, 25, 90, seed=2)
     ones_n, ones_k = np.ones(25, np.float32), np.ones(90, np.float32)
