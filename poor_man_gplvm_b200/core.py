@@ -298,6 +298,7 @@ class PoissonGPLVMJump1D:
         state['adam_runner'] = None
         state['opt_state_init_fun'] = None
         state.pop('_opt_state', None)          # device tensors; fit_em re-initialises Adam anyway (core.py:847)
+        state.pop('_pack_cache', None)         # device tensors; rebuilt on demand
         return state
 
     def __setstate__(self, state):
@@ -350,10 +351,18 @@ class PoissonGPLVMJump1D:
         mv = hyperparam.get('movement_variance', self.movement_variance)
         pmj = hyperparam.get('p_move_to_jump', self.p_move_to_jump)
         pjm = hyperparam.get('p_jump_to_move', self.p_jump_to_move)
+        # K x K host work (kernel matrices, band factorisation, stationary solve): a few ms, reused by repeated
+        # fit / decode calls with the same dynamics
+        key = (float(mv), float(pmj), float(pjm), id(self.custom_transition_kernel), self.n_latent_bin,
+               str(self.device))
+        cached = getattr(self, "_pack_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         P, logP, M, logM = gpk.create_transition_prob_1d(self.possible_latent_bin, self.possible_dynamics, mv, pmj, pjm,
                                                          custom_kernel=self.custom_transition_kernel)
         host = gpk.move_operator_host(self.n_latent_bin, mv, self.custom_transition_kernel, p_move_to_jump=pmj)
         op = ops.MoveOperator(host, M, self.device, P0=P[0])
+        self._pack_cache = (key, (P, logP, M, logM, op))
         return P, logP, M, logM, op
 
     def _masks(self, ma_neuron, ma_latent, T):

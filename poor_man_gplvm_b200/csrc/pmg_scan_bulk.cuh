@@ -46,7 +46,7 @@ struct BulkGeo {
     return round4(2 * R) + 2 * exf() + R * KP + OB * 2 * KP;
   }
   __host__ __device__ static int bwd_chain_floats(int R, int OB) {
-    return round4(2 * R) + 2 * exf() + R * 3 * KP + OB * KP;
+    return round4(2 * R) + 2 * exf() + R * 3 * KP + OB * KP + KP;   // + one fp32 row: transpose staging
   }
 };
 
@@ -258,6 +258,23 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
   float* exch = base + round4(2 * R);
   float* ring = exch + 2 * exf;                      // slot: [ll KP | alpha move KP | alpha jump KP]
   __half* outh = reinterpret_cast<__half*>(ring + (size_t)R * 3 * KP);   // 2 buffers x (hi KP | lo KP) halves
+  float* trow = ring + (size_t)R * 3 * KP + (size_t)OB * KP;             // fp32 row: lane-blocked -> coalesced
+  // fp32 output rows (gamma, gamma_lat, r: last EM iteration / decode): each lane owns Q consecutive latent
+  // bins, so direct stores would scatter 4-byte pieces; the row goes through shared memory and leaves as
+  // 16-byte stores of consecutive lanes (K % 4 == 0 and 16-byte aligned rows; otherwise scalar, still coalesced)
+  const bool vec_rows = (K & 3) == 0;
+  auto store_row = [&](float* dst, const float (&v)[Q], float scale) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) trow[x0 + q] = v[q] * scale;
+    __syncwarp();
+    if (vec_rows && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int j = lane * 4; j < K; j += 128)
+        *reinterpret_cast<float4*>(dst + j) = *reinterpret_cast<const float4*>(trow + j);
+    } else {
+      for (int j = lane; j < K; j += 32) dst[j] = trow[j];
+    }
+    __syncwarp();
+  };
   for (int i = lane; i < 2 * exf; i += 32) exch[i] = 0.f;
   for (int i = lane; i < R * 3 * KP; i += 32) ring[i] = ((i / KP) % 3 == 0) ? -INFINITY : 0.f;
   if (lane == 0) {
@@ -428,17 +445,19 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
       float* g = p.gamma ? p.gamma + (size_t)t * 2 * K : nullptr;
       float* gl_ = p.gamma_lat ? p.gamma_lat + (size_t)t * K : nullptr;
       __half* oh = outh + (size_t)out_par * 2 * KP;
+      float gsum[Q];
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const float ga = g0[q] * inv, gb = g1[q] * inv;
         const float gs = ga + gb;
+        gsum[q] = gs;
         tw_acc[q] += gs;
         const __half h = __float2half_rn(gs);
         oh[x0 + q] = h;
         oh[KP + x0 + q] = __float2half_rn(gs - __half2float(h));
-        if (g && x0 + q < K) { g[x0 + q] = ga; g[K + x0 + q] = gb; }
-        if (gl_ && x0 + q < K) gl_[x0 + q] = gs;
       }
+      if (g) { store_row(g, g0, inv); store_row(g + K, g1, inv); }
+      if (gl_) store_row(gl_, gsum, 1.f);
       if (p.gamma16) {
         fence_proxy_async();
         __syncwarp();
@@ -455,9 +474,8 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
       }
       if (p.r_out && i != 0) {
         float* ro = p.r_out + (size_t)(t + 1) * 2 * K;
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-          if (x0 + q < K) { ro[x0 + q] = r0[q] * r_scale; ro[K + x0 + q] = r1[q] * r_scale; }
+        store_row(ro, r0, r_scale);
+        store_row(ro + K, r1, r_scale);
       }
     } else if (t == cr.t_end && p.beta_halo) {
       float* o = p.beta_halo + (size_t)cr.s * 2 * K;

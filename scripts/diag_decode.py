@@ -11,7 +11,12 @@ dev = torch.device("cuda")
 d = make_dataset_torch(T, N, K, dev, seed=1234)
 y = d["y"].to(torch.float32).contiguous()
 model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=10.0, movement_variance=1.0, device=dev)
-tun = (torch.rand((K, N), device=dev) + 0.05)
+em = model.fit_em(y, n_iter=6, return_device=True)
+tun = em["tuning"] if isinstance(em["tuning"], torch.Tensor) else torch.as_tensor(em["tuning"], device=dev)
+del em
+marks = []
+def hook(name):
+    torch.cuda.synchronize(); marks.append((name, time.perf_counter()))
 def sync(): torch.cuda.synchronize(); return time.perf_counter()
 for rep in range(3):
     t0 = sync()
@@ -20,8 +25,11 @@ for rep in range(3):
     t1 = sync()
     es = EStep(y, op, ma_n, ma_l, 1.0)
     t2 = sync()
+    ops.PHASE_HOOK = hook; marks.clear(); marks.append(("start", time.perf_counter()))
     res = es.run(tun, want_gamma=True, want_gamma_lat=True, want_dyn=True, want_r=True)
-    t3 = sync()
+    t3 = sync(); ops.PHASE_HOOK = None; marks.append(("end", t3))
+    print("   run phases:", " ".join("%s %.2f" % (n1, (t1 - t0) * 1e3) for (n0, t0), (n1, t1) in zip(marks[:-1], marks[1:])),
+          "relays", res.n_relay_fwd, res.n_relay_bwd)
     lg = torch.log(res.gamma)
     t4 = sync()
     log_acc = model._transition_counts(es, res, logP, logM)
