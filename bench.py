@@ -254,8 +254,9 @@ def run_ours(args):
     N, K, T, ls, mv = WORKLOADS[args.workload]
     if args.bins:
         T = args.bins
-    # weak scaling: every rank owns T bins of the same synthetic process (independent time blocks)
-    data = make_dataset_torch(T, N, K, dev, seed=1234 + rank)
+    # weak scaling: every rank owns T bins of ONE recording (same neurons and tuning curves on every rank; each
+    # block has its own latent trajectory and spikes)
+    data = make_dataset_torch(T, N, K, dev, seed=1234 + rank, tuning_seed=1234)
     y_dev = data["y"].to(torch.float32).contiguous()
     model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, movement_variance=mv, device=dev)
     rng = np.random.default_rng(1)

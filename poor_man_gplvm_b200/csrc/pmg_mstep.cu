@@ -12,6 +12,7 @@
 #include <cooperative_groups.h>
 
 #include "pmg_common.cuh"
+#include <cstdlib>
 
 namespace pmg {
 
@@ -240,6 +241,251 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mstep_adam_kernel(const MstepPa
   if (p.tuning_out) eval(false, 1, lc, ec, true);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Same optimisation with the grid-wide reduction taken off the critical path.
+//
+// The gradient is separable per neuron; only the STOP decision needs the global loss.  Every CTA therefore
+// keeps stepping on its own tile while the loss of step j is reduced: it publishes its partial of every step
+// (per-step slots + per-step arrival counters) and evaluates the reference's stop rule for step i - LAG, by
+// which time all partials of that step have long arrived.  The last LAG+1 optimiser states (W, mu, nu) of the
+// tile live in shared memory; when the rule says "stop before update j", the state after j updates is
+// restored.  Partials, their reduction order and all arithmetic are those of mstep_adam_kernel, so both
+// kernels return the same bits.  One tile per CTA (N <= 4 * #resident CTAs), state of a tile in shared memory.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MS_LAG = 4;        // a step's stop rule is evaluated at least this many steps later
+constexpr int MS_BATCH = 4;      // ... and MS_BATCH steps at a time (one warp per step)
+
+template <int LT>
+__global__ void __launch_bounds__(LT, 1) mstep_adam_lag_kernel(const MstepParams p, unsigned* arrived) {
+  extern __shared__ float smem[];
+  const int K = p.K, B = p.B, N = p.N, Bs = p.Bs;
+  const int tid = threadIdx.x;
+  constexpr int R = MS_LAG + MS_BATCH + 1;
+  const int BT = B * MS_NT;
+  float* phiS = smem;                                   // [K][Bs] when phi_in_smem
+  float* eS = phiS + (p.phi_in_smem ? (((size_t)K * Bs + 3) & ~(size_t)3) : 0);   // [K][NT], 16B aligned
+  const int parts = B >= LT ? 1 : LT / B;
+  float* gS = eS + (size_t)K * MS_NT;                   // [parts][B][NT]
+  float* ywS = gS + (size_t)parts * BT;                 // [K][NT]
+  float* twS = ywS + (size_t)K * MS_NT;                 // [K]
+  float* Wr = twS + ((K + 3) & ~3);                     // [R][B][NT] ring of optimiser states
+  float* Mr = Wr + (size_t)R * BT;
+  float* Vr = Mr + (size_t)R * BT;
+  __shared__ double redD[2][2][LT / 32];            // [step parity][loss, err][warp]
+  __shared__ float bL[MS_BATCH], bE[MS_BATCH];
+
+  const int n0 = blockIdx.x * MS_NT;
+  if (p.phi_in_smem) {
+    for (int i = tid; i < K * B; i += LT) phiS[(size_t)(i / B) * Bs + (i % B)] = p.Phi[i];
+  }
+  for (int i = tid; i < BT; i += LT) {
+    const int b = i / MS_NT, nt = i % MS_NT;
+    const bool ok = n0 + nt < N;
+    const size_t gi = (size_t)b * N + n0 + nt;
+    Wr[i] = ok ? p.W[gi] : 0.f;
+    Mr[i] = ok ? p.mu[gi] : 0.f;
+    Vr[i] = ok ? p.nu[gi] : 0.f;
+  }
+  for (int i = tid; i < K * MS_NT; i += LT) {
+    const int k = i / MS_NT, nt = i % MS_NT;
+    ywS[i] = (n0 + nt < N) ? p.yw[(size_t)k * N + n0 + nt] : 0.f;
+  }
+  for (int k = tid; k < K; k += LT) twS[k] = p.tw[k];
+  __syncthreads();
+  const float* phi = p.phi_in_smem ? phiS : p.Phi;
+  const int ldphi = p.phi_in_smem ? Bs : B;
+  const float inv_s2 = 1.f / (p.prior_std * p.prior_std);
+  const float log_norm = logf(6.283185307179586f * p.prior_std * p.prior_std);
+  const int count0 = *p.count;
+
+  // loss / gradient at ring state `cur`; with `update` the Adam step goes to ring state `nxt`
+  auto eval = [&](int cur, int nxt, bool update, int step_count, double& loss_cta, double& err_cta,
+                  bool write_tuning) {
+    const float bc1 = 1.f - powf(p.b1, (float)step_count);
+    const float bc2 = 1.f - powf(p.b2, (float)step_count);
+    const float* wS = Wr + (size_t)cur * BT;
+    float loss_t = 0.f;
+    for (int k = tid; k < K; k += LT) {
+      float z[MS_NT];
+#pragma unroll
+      for (int nt = 0; nt < MS_NT; ++nt) z[nt] = 0.f;
+      const float* prow = phi + (size_t)k * ldphi;
+      for (int b = 0; b < B; ++b) {
+        const float ph = prow[b];
+        const float4 w4 = *reinterpret_cast<const float4*>(wS + b * MS_NT);
+        z[0] = fmaf(ph, w4.x, z[0]); z[1] = fmaf(ph, w4.y, z[1]);
+        z[2] = fmaf(ph, w4.z, z[2]); z[3] = fmaf(ph, w4.w, z[3]);
+      }
+      const float twk = twS[k];
+#pragma unroll
+      for (int nt = 0; nt < MS_NT; ++nt) {
+        float e = 0.f;
+        if (n0 + nt < N) {
+          const float pf = softplus_f(z[nt]);
+          if (write_tuning) {
+            p.tuning_out[(size_t)k * N + n0 + nt] = pf;
+          } else {
+            const float ywv = ywS[k * MS_NT + nt];
+            const float pfe = pf + kLamFloor;
+            e = (ywv / pfe - twk) * sigmoid_f(z[nt]);
+            const float fit = (ywv == 0.f) ? 0.f : ywv * logf(pfe);
+            loss_t -= fit - pf * twk;
+          }
+        }
+        eS[k * MS_NT + nt] = e;
+      }
+    }
+    if (write_tuning) return;
+    __syncthreads();
+    if (B >= LT) {
+      for (int b = tid; b < B; b += LT) {
+        float g[MS_NT] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < K; ++k) {
+          const float ph = phi[(size_t)k * ldphi + b];
+          const float4 e4 = *reinterpret_cast<const float4*>(eS + k * MS_NT);
+          g[0] = fmaf(ph, e4.x, g[0]); g[1] = fmaf(ph, e4.y, g[1]);
+          g[2] = fmaf(ph, e4.z, g[2]); g[3] = fmaf(ph, e4.w, g[3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < MS_NT; ++nt) gS[b * MS_NT + nt] = g[nt];
+      }
+    } else if (tid < parts * B) {
+      const int part = tid / B, b = tid % B;
+      const int kb = (int)(((int64_t)K * part) / parts), ke = (int)(((int64_t)K * (part + 1)) / parts);
+      float g[MS_NT] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = kb; k < ke; ++k) {
+        const float ph = phi[(size_t)k * ldphi + b];
+        const float4 e4 = *reinterpret_cast<const float4*>(eS + k * MS_NT);
+        g[0] = fmaf(ph, e4.x, g[0]); g[1] = fmaf(ph, e4.y, g[1]);
+        g[2] = fmaf(ph, e4.z, g[2]); g[3] = fmaf(ph, e4.w, g[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < MS_NT; ++nt) gS[((size_t)part * B + b) * MS_NT + nt] = g[nt];
+    }
+    __syncthreads();
+    float err_t = 0.f;
+    for (int i = tid; i < BT; i += LT) {
+      const int nt = i % MS_NT;
+      if (n0 + nt >= N) continue;
+      const int b = i / MS_NT;
+      float gsum = 0.f;
+      for (int pz = 0; pz < parts; ++pz) gsum += gS[((size_t)pz * B + b) * MS_NT + nt];
+      const float w = wS[i];
+      const float g = -gsum + w * inv_s2;
+      err_t = fmaf(g, g, err_t);
+      loss_t += 0.5f * (log_norm + w * w * inv_s2);
+      if (update) {
+        const float m = p.b1 * Mr[(size_t)cur * BT + i] + (1.f - p.b1) * g;
+        const float v = p.b2 * Vr[(size_t)cur * BT + i] + (1.f - p.b2) * g * g;
+        Mr[(size_t)nxt * BT + i] = m; Vr[(size_t)nxt * BT + i] = v;
+        Wr[(size_t)nxt * BT + i] = w - p.lr * ((m / bc1) / (sqrtf(v / bc2) + p.eps));
+      }
+    }
+    loss_cta = (double)loss_t;      // per-thread partials, reduced by publish()
+    err_cta = (double)err_t;
+  };
+
+  // per-CTA partial of a step -> its slot, then the step's arrival counter.  The last thread publishes (its warp
+  // has no rows of Phi in phase 1 when K <= LT - 32), nobody waits for its fence: the staging is double-buffered
+  // by step parity and the ring writes of this step are ordered by the barrier below.
+  auto publish = [&](int slot, double loss_thr, double err_thr) {
+    const int par = slot & 1;
+    double a = warp_sum_d(loss_thr), b = warp_sum_d(err_thr);
+    if ((tid & 31) == 0) { redD[par][0][tid >> 5] = a; redD[par][1][tid >> 5] = b; }
+    __syncthreads();
+    if (tid == LT - 1) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int w = 0; w < LT / 32; ++w) { s0 += redD[par][0][w]; s1 += redD[par][1][w]; }
+      p.partials[((size_t)slot * gridDim.x + blockIdx.x) * 2 + 0] = s0;
+      p.partials[((size_t)slot * gridDim.x + blockIdx.x) * 2 + 1] = s1;
+      __threadfence();
+      atomicAdd(arrived + slot, 1u);
+    }
+  };
+  // global loss / gradient norm of steps first .. first+n-1, one warp per step (waits for every CTA's partial;
+  // fixed summation order: the same bits in every CTA, hence the same decisions)
+  auto resolve = [&](int first, int n) {
+    const int w = tid >> 5, ln = tid & 31;
+    if (w < n) {
+      const int slot = first + w;
+      if (ln == 0) {
+        while (*(volatile unsigned*)(arrived + slot) < gridDim.x) { }
+        __threadfence();
+      }
+      __syncwarp();
+      double s0 = 0.0, s1 = 0.0;
+      const double* src = p.partials + (size_t)slot * gridDim.x * 2;
+      for (unsigned c = ln; c < gridDim.x; c += 32) {
+        s0 += __ldcg(src + 2 * c);
+        s1 += __ldcg(src + 2 * c + 1);
+      }
+      s0 = warp_sum_d(s0);
+      s1 = warp_sum_d(s1);
+      if (ln == 0) { bL[w] = (float)s0; bE[w] = sqrtf((float)s1); }
+    }
+    __syncthreads();
+  };
+
+  double lc, ec;
+  eval(0, 0, false, count0 + 1, lc, ec, false);
+  publish(0, lc, ec);
+  int done = 0;                     // updates performed by this CTA (slots 0 .. done are published)
+  int decided = 0;                  // stop rule evaluated for steps 0 .. decided-1 (all said "continue")
+  int stop_at = -1;
+  float l_prev = 0.f, l_fin = 0.f, e_fin = 0.f;
+  while (stop_at < 0) {
+    // rules are evaluated MS_BATCH steps at a time once the newest of them is MS_LAG steps old (and for every
+    // remaining step once no further update is possible)
+    const bool drain = done >= p.maxiter - 1;
+    while (stop_at < 0 && (decided + MS_BATCH - 1 <= done - MS_LAG || drain)) {
+      int n = done - decided + 1;
+      if (n > MS_BATCH) n = MS_BATCH;
+      resolve(decided, n);
+      for (int j = 0; j < n && stop_at < 0; ++j) {
+        const float l = bL[j], e = bE[j];
+        if (blockIdx.x == 0 && tid == 0) { p.loss_hist[decided] = l; p.err_hist[decided] = e; }
+        // reference loop: at its first test loss_prev == loss
+        const float rel = decided == 0 ? 0.f : fabsf(l - l_prev) / fmaxf(fabsf(l), 1e-8f);
+        const bool cont = decided < p.maxiter - 1 && (decided < p.min_iters || rel > p.tol);
+        l_prev = l;
+        if (!cont) { stop_at = decided; l_fin = l; e_fin = e; }
+        else ++decided;
+      }
+      __syncthreads();              // bL / bE are rewritten by the next batch
+    }
+    if (stop_at >= 0) break;
+    eval(done % R, (done + 1) % R, true, count0 + done + 1, lc, ec, false);
+    publish(done + 1, lc, ec);
+    ++done;
+  }
+  // state after stop_at updates
+  const int fin = stop_at % R;
+  for (int i = tid; i < BT; i += LT) {
+    const int b = i / MS_NT, nt = i % MS_NT;
+    if (n0 + nt >= N) continue;
+    const size_t gi = (size_t)b * N + n0 + nt;
+    p.W[gi] = Wr[(size_t)fin * BT + i];
+    p.mu[gi] = Mr[(size_t)fin * BT + i];
+    p.nu[gi] = Vr[(size_t)fin * BT + i];
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    *p.n_iter_out = stop_at + 1;
+    *p.count = count0 + stop_at;
+    p.final_out[0] = l_fin;
+    p.final_out[1] = e_fin;
+  }
+  if (p.tuning_out) eval(fin, fin, false, 1, lc, ec, true);
+}
+
+template <int LT>
+static size_t mstep_lag_smem(int K, int B, bool phi_in_smem, int Bs) {
+  const int parts = B >= LT ? 1 : LT / B;
+  size_t f = (size_t)K * MS_NT + (size_t)parts * B * MS_NT + (size_t)K * MS_NT + (size_t)((K + 3) & ~3) +
+             (size_t)3 * (MS_LAG + MS_BATCH + 1) * B * MS_NT;
+  if (phi_in_smem) f += ((size_t)K * Bs + 3) & ~(size_t)3;
+  return f * sizeof(float);
+}
+
 // tuning = softplus(Phi W): small standalone kernel (used outside the M-step)
 __global__ void tuning_softplus_kernel(int K, int B, int N, const float* __restrict__ Phi,
                                        const float* __restrict__ W, float* __restrict__ tuning) {
@@ -262,8 +508,8 @@ static size_t mstep_smem(int K, int B, bool phi_in_smem, int Bs) {
 
 extern "C" int64_t pmg_mstep_workspace_bytes(int K, int B, int N, int maxiter) {
   (void)K; (void)B; (void)N;
-  // partials for up to 1024 CTAs + barrier word (256-byte header)
-  return 256 + (int64_t)(maxiter + 1) * 1024 * 2 * (int64_t)sizeof(double);
+  // barrier word (256-byte header) + partials for up to 1024 CTAs + per-step arrival counters
+  return 256 + (int64_t)(maxiter + 1) * 1024 * 2 * (int64_t)sizeof(double) + (int64_t)(maxiter + 1) * 4 + 256;
 }
 
 extern "C" int pmg_mstep_adam(int K, int B, int N, const float* Phi, const float* yw, const float* tw,
@@ -294,6 +540,32 @@ extern "C" int pmg_mstep_adam(int K, int B, int N, const float* Phi, const float
   PMG_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
   PMG_CUDA_CHECK(cudaMemsetAsync(loss_hist, 0, sizeof(float) * maxiter, st));
   PMG_CUDA_CHECK(cudaMemsetAsync(err_hist, 0, sizeof(float) * maxiter, st));
+  {
+    // lagged-decision kernel: one tile per CTA, all CTAs resident, tile state + operands in shared memory
+    const char* lag_s = std::getenv("PMG_MSTEP_LAG");      // 0 = the barrier-per-step kernel (cross-check)
+    const int lag_env = lag_s ? std::atoi(lag_s) : 1;
+    const int ntiles_l = (N + MS_NT - 1) / MS_NT;
+    constexpr int LT = 512;         // threads per CTA of the lagged kernel (one round over K <= 512 rows of Phi)
+    int Bs_l = B | 1;
+    bool phi_l = mstep_lag_smem<LT>(K, B, true, Bs_l) <= 200 * 1024;
+    const size_t smem_l = mstep_lag_smem<LT>(K, B, phi_l, Bs_l);
+    int dev_l = 0, sms_l = 0, per_l = 0;
+    PMG_CUDA_CHECK(cudaGetDevice(&dev_l));
+    PMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms_l, cudaDevAttrMultiProcessorCount, dev_l));
+    if (lag_env && smem_l <= 200 * 1024) {
+      PMG_CUDA_CHECK(cudaFuncSetAttribute(mstep_adam_lag_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+      PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_l, mstep_adam_lag_kernel<LT>, LT, smem_l));
+      if (per_l >= 1 && ntiles_l <= sms_l * per_l && ntiles_l <= 1024) {
+        p.Bs = Bs_l; p.phi_in_smem = phi_l;
+        unsigned* arrived = (unsigned*)((char*)workspace + 256 + (size_t)(maxiter + 1) * 1024 * 2 * sizeof(double));
+        PMG_CUDA_CHECK(cudaMemsetAsync(arrived, 0, (size_t)(maxiter + 1) * sizeof(unsigned), st));
+        void* args_l[] = {(void*)&p, (void*)&arrived};
+        PMG_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)mstep_adam_lag_kernel<LT>, dim3(ntiles_l), dim3(LT),
+                                                   args_l, smem_l, st));
+        return PMG_OK;
+      }
+    }
+  }
   PMG_CUDA_CHECK(cudaFuncSetAttribute(mstep_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0, per_sm = 0;
   PMG_CUDA_CHECK(cudaGetDevice(&dev));

@@ -41,16 +41,19 @@ def make_dataset(T, n_neuron, n_latent_bin, seed=0, p_jump=0.01):
     return {"y": y, "latent": lat, "jump": jumps, "tuning_true": tuning}
 
 
-def make_dataset_torch(T, n_neuron, n_latent_bin, device, seed=0, p_jump=0.01):
+def make_dataset_torch(T, n_neuron, n_latent_bin, device, seed=0, p_jump=0.01, tuning_seed=None):
     """Device-side generator for the large bench configs (different PRNG stream
     from ``make_dataset``; same distribution).  The walk is generated as a
-    cumulative sum of +-1 steps reflected into ``0..K-1`` between jump times."""
+    cumulative sum of +-1 steps reflected into ``0..K-1`` between jump times.
+    tuning_seed: seed of the tuning curves (default: ``seed``).  Time-sharded ranks pass the same
+    ``tuning_seed`` and different ``seed``s: blocks of ONE recording (same neurons, same tuning), each
+    with its own latent trajectory and spikes."""
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     K = n_latent_bin
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed if tuning_seed is None else tuning_seed)
     tuning = torch.from_numpy(bump_tuning(K, n_neuron, rng)).to(device)
     steps = torch.randint(-1, 2, (T,), generator=g, device=device)
     jumps = torch.rand(T, generator=g, device=device) < p_jump

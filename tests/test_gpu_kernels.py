@@ -371,6 +371,45 @@ def test_mstep_adam_matches_oracle(ops, K, N, ls):
     assert np.max(np.abs(host(W) - want2["params"])) < 4e-4
 
 
+@pytest.mark.parametrize("K,N,ls,maxiter,tol", [(100, 30, 10.0, 1000, 1e-6), (400, 500, 10.0, 300, 1e-6),
+                                                  (64, 7, 4.0, 40, -1.0), (48, 20, 1.0, 12, 1e-3)])
+def test_mstep_lagged_kernel_matches_barrier_kernel(ops, K, N, ls, maxiter, tol):
+    """The M-step kernel that keeps stepping while the stop rule of step i-4 is being reduced (and rolls back to
+    the step the rule selects) against the barrier-per-step kernel: same rule, same step count, same optimum up
+    to the rounding of two separately compiled fp32 loops (which Adam amplifies to ~1e-3 in W after hundreds of
+    steps)."""
+    import os
+    from poor_man_gplvm_b200 import gp_kernel as gpk
+    rng = np.random.default_rng(K + N)
+    basis = gpk.generate_basis(ls, K)
+    B = basis.shape[1]
+    tw = (rng.random(K) * 50 + 1).astype(np.float32)
+    yw = (rng.random((K, N)) * tw[:, None] * 1.5).astype(np.float32)
+    W0 = rng.standard_normal((B, N)).astype(np.float32)
+    outs = []
+    for lag in ("0", "1"):
+        os.environ["PMG_MSTEP_LAG"] = lag
+        try:
+            W = dev(W0.copy())
+            st = ops.AdamState(W)
+            res = []
+            for rep in range(2):                      # second call: Adam state carried over (count > 0)
+                lh, eh, n_it, fin, tuning = ops.mstep_adam(dev(basis), dev(yw), dev(tw), W, st, 1.0, 0.01, maxiter, tol)
+                res.append([host(x).copy() for x in (lh, eh, n_it, fin, tuning, W, st.mu, st.nu, st.count)])
+            outs.append(res)
+        finally:
+            os.environ.pop("PMG_MSTEP_LAG", None)
+    for a, b in zip(outs[0], outs[1]):
+        na, nb = int(a[2][0]), int(b[2][0])
+        assert 1 <= nb <= maxiter and abs(na - nb) <= max(1, na // 50)
+        assert int(a[8][0]) - na == int(b[8][0]) - nb                       # Adam count advanced by n_iter - 1
+        n = min(na, nb)
+        assert np.max(np.abs(a[0][:n] - b[0][:n]) / np.abs(a[0][:n])) < 1e-5  # loss history
+        assert np.all(b[0][nb:] == 0) and np.all(b[1][nb:] == 0)             # nothing written past the stop
+        assert np.max(np.abs(a[4] - b[4]) / np.maximum(a[4], 1e-3)) < 2e-3     # tuning
+        assert np.max(np.abs(a[5] - b[5])) < 1e-2                              # W
+
+
 def test_mstep_default_stop_rule_close_to_oracle(ops):
     rng = np.random.default_rng(9)
     K, N = 60, 12

@@ -51,9 +51,11 @@ def _worker(rank, world, port, y, lp0, params, N, K, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_time_sharded_fit_matches_single_gpu():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4])
+def test_time_sharded_fit_matches_single_gpu(world):
+    """world = 4 exercises interior ranks (two neighbours, both boundary exchanges)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import poor_man_gplvm_b200 as pmg
     N, K, T = 30, 96, 6000
     d = make_dataset(T, N, K, seed=21)
@@ -66,24 +68,25 @@ def test_two_rank_time_sharded_fit_matches_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, d["y"], lp0, params, N, K, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, d["y"], lp0, params, N, K, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = dict(q.get(timeout=600) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    for r in range(2):
+    for r in range(world):
         assert isinstance(out[r], dict), out[r]
     lml1 = np.array(single["log_marginal_l"])
-    for r in range(2):
+    for r in range(world):
         assert np.max(np.abs(out[r]["lml"] - lml1) / np.abs(lml1)) < 1e-5
         assert np.max(np.abs(out[r]["tuning"] - single["tuning"]) / single["tuning"]) < 1e-3
         assert abs(out[r]["dec_lml"] - sdec["log_marginal_final"]) < 1e-5 * abs(sdec["log_marginal_final"])
         assert np.max(np.abs(out[r]["pj"] - np.asarray(sdec["p_joint_latent"]))) < 1e-5
-    assert np.array_equal(out[0]["tuning"], out[1]["tuning"])        # replicated M-step: identical on all ranks
-    post = np.concatenate([out[0]["post"], out[1]["post"]])
-    dyn = np.concatenate([out[0]["dyn"], out[1]["dyn"]])
+    for r in range(1, world):
+        assert np.array_equal(out[0]["tuning"], out[r]["tuning"])    # replicated M-step: identical on all ranks
+    post = np.concatenate([out[r]["post"] for r in range(world)])
+    dyn = np.concatenate([out[r]["dyn"] for r in range(world)])
     assert np.max(np.abs(post - single["posterior_latent_marg"])) < 2e-5
     assert np.max(np.abs(dyn - single["posterior_dynamics_marg"])) < 2e-5
-    dpost = np.concatenate([out[0]["dec_post"], out[1]["dec_post"]])
+    dpost = np.concatenate([out[r]["dec_post"] for r in range(world)])
     assert np.max(np.abs(dpost - sdec["posterior_latent_marg"])) < 2e-5
