@@ -49,7 +49,7 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of the hot kernels from the committed ncu --set full summary (headline workload)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_summary_v3.csv")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_summary_v4.csv")
     out = {}
     try:
         import csv
@@ -368,7 +368,7 @@ def run_ours(args):
     if dominant:
         r = dict(roof_all[dominant])
         r.update({"phase": dominant, "peak_source": pk["src"],
-                  "traffic_source": "profiles/r01_ncu_full_summary_v3.csv (dram__bytes_read.sum + dram__bytes_write.sum "
+                  "traffic_source": "profiles/r01_ncu_full_summary_v4.csv (dram__bytes_read.sum + dram__bytes_write.sum "
                                     "of one ncu --set full capture of this kernel at this workload)"
                                     if r.get("traffic") else None})
         roofline = r

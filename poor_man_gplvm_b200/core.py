@@ -205,7 +205,7 @@ class EMLoop:
         while the host synchronises (the one synchronisation per EM iteration).  They only read what the
         backward pass wrote; if a seam then fails and chains are re-run, the Adam state is restored from a
         snapshot and the next iteration recomputes them.  Pass False for the last iteration of a fit."""
-        spec_ok = bool(speculate and self.use_tc)
+        spec_ok = bool(speculate and self.use_tc and os.environ.get("PMG_NO_SPECULATE", "0") == "0")
         if self._spec is not None:
             m_res, self._spec = self._spec, None
         else:
