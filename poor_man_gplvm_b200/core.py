@@ -136,6 +136,7 @@ class EMLoop:
         self._tuning = torch.empty((2, self.Phi.shape[0], model.n_neuron), dtype=torch.float32, device=self.W.device)
         self._tuning_i = 0
         self._spec = None                  # M-step result enqueued ahead for the next iteration (see iteration)
+        self._last_repaired = False
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
         self.use_tc = self.es.y16 is not None and self.es.y16.exact
         T_core, K = y_dev.shape[0], op.K
@@ -193,6 +194,21 @@ class EMLoop:
         ops.phase("stats")
         m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
                                self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
+        if self.shard.active:
+            # The M-step is replicated.  Every rank must use the same tuning bit for bit (ranks recompute their
+            # neighbours' halo bins and verify boundary seams at 1e-5) and keep the same optimiser state, so
+            # rank 0's result is broadcast: 1.2 MB, one collective, instead of relying on every rank's inputs
+            # and arithmetic being bit-identical.
+            st = self.state
+            parts = [m_res[4], self.W, st.mu, st.nu]
+            flat = torch.cat([t.reshape(-1) for t in parts] + [st.count.to(torch.float32)])
+            self.shard.broadcast_(flat, 0)
+            o = 0
+            for t in parts:
+                n = t.numel()
+                t.copy_(flat[o:o + n].view(t.shape))
+                o += n
+            st.count.copy_(flat[o:o + 1].to(torch.int32))
         ops.phase("mstep")
         return m_res
 
@@ -205,7 +221,10 @@ class EMLoop:
         while the host synchronises (the one synchronisation per EM iteration).  They only read what the
         backward pass wrote; if a seam then fails and chains are re-run, the Adam state is restored from a
         snapshot and the next iteration recomputes them.  Pass False for the last iteration of a fit."""
-        spec_ok = bool(speculate and self.use_tc and os.environ.get("PMG_NO_SPECULATE", "0") == "0")
+        # (not right after an iteration that needed seam repairs: the next one probably does too, and a rolled
+        # back M-step is wasted work)
+        spec_ok = bool(speculate and self.use_tc and not self._last_repaired
+                       and os.environ.get("PMG_NO_SPECULATE", "0") == "0")
         if self._spec is not None:
             m_res, self._spec = self._spec, None
         else:
@@ -221,6 +240,7 @@ class EMLoop:
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16,
                           before_sync=enqueue_next if spec_ok else None)
+        self._last_repaired = bool(res.repaired)
         if "m_res" in nxt:
             if res.repaired:
                 W, mu, nu, count, self._n_mstep, self._hist, self._tuning_i = nxt["snap"]

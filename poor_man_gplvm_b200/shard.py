@@ -99,6 +99,11 @@ class TimeShard:
             t.copy_(flat[o:o + n].reshape(t.shape).to(t.dtype))
             o += n
 
+    def broadcast_(self, t, src=0):
+        """In-place broadcast from rank `src` of the group."""
+        if self.active:
+            dist.broadcast(t, src=self._peer(src), group=self.group)
+
     def allreduce_max_(self, t):
         """In-place element-wise maximum over ranks."""
         if self.active:
