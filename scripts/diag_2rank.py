@@ -10,7 +10,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 T, N, K = int(os.environ.get("T", 1000000)), 500, 400
-y = make_dataset_torch(T, N, K, dev, seed=1234 + rank, tuning_seed=1234)["y"].to(torch.float32).contiguous()
+y = make_dataset_torch(T, N, K, dev, seed=int(os.environ.get("SEED", 1234)) + rank, tuning_seed=1234)["y"].to(torch.float32).contiguous()
 model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=10.0, movement_variance=1.0, device=dev)
 model.params = np.random.default_rng(1).standard_normal((model.n_basis, N)).astype(np.float32)
 P, logP, M, logM, op = model._transition_pack({})
