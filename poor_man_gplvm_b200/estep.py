@@ -313,37 +313,37 @@ class EStep:
             # all at once (on all ranks), from a snapshot of its neighbour's current boundary message; the
             # seams are then re-verified against the messages those restarts produced.  Each sweep extends
             # the effective warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length.
-            redo_bwd = False
-            for _ in range(S * self.shard.world + 1 if any_f else 0):
-                bad = torch.nonzero(ef > self.seam_tol).flatten() + self.f_lo
-                if self.shard.max_int(bad.numel(), self.dev) == 0:
+            # One sweep = forward restarts, then the backward pass of (a) the chains whose filtered posterior
+            # just changed -- from their own, already verified, incoming beta -- and (b) the chains whose
+            # incoming beta was off -- from the neighbour's; other chains' backward results do not depend on
+            # the re-run chains (beta does not involve alpha; normalisers are scale only).  One verdict
+            # (synchronisation + collective) per sweep.
+            repaired = bool(any_f or any_b)
+            for _ in range(S * self.shard.world + 2):
+                if not (any_f or any_b):
                     break
-                redo_bwd = True
-                n_relay_f += int(bad.numel())
-                if bad.numel():
-                    ids = bad.to(device=self.dev, dtype=torch.int32)
+                bad_f = torch.nonzero(ef > self.seam_tol).flatten() + self.f_lo
+                bad_b = torch.nonzero(eb > self.seam_tol).flatten()
+                n_relay_f += int(bad_f.numel())
+                n_relay_b += int(bad_b.numel())
+                if bad_f.numel():
+                    ids = bad_f.to(device=self.dev, dtype=torch.int32)
                     self.halo_state[ids.long()] = self.truth[ids.long()]      # carry snapshot = new "estimate"
                     fwd(mode=1, ids=ids)
                 self._exchange_fwd(compact, nxt)
+                if bad_b.numel():
+                    idb = bad_b.to(device=self.dev)
+                    self.beta_halo[idb] = self.beta_end[idb + 1]
+                both = torch.unique(torch.cat([bad_f, bad_b]))
+                if both.numel():
+                    bwd(mode=1, ids=both.to(device=self.dev, dtype=torch.int32))
+                self._exchange_bwd(nxt)
                 self._check_fwd(compact)
-                ef = self._read_err()[self.f_lo:S].clone()
-            if redo_bwd:
-                bwd()
-                self._exchange_bwd(nxt)
                 self._check_bwd()
-                eb = self._read_err()[S:S + self.b_hi].clone()
-            for _ in range(S * self.shard.world + 1 if (any_b or redo_bwd) else 0):
-                bad = torch.nonzero(eb > self.seam_tol).flatten()
-                if self.shard.max_int(bad.numel(), self.dev) == 0:
-                    break
-                n_relay_b += int(bad.numel())
-                if bad.numel():
-                    ids = bad.to(device=self.dev, dtype=torch.int32)
-                    self.beta_halo[ids.long()] = self.beta_end[ids.long() + 1]
-                    bwd(mode=1, ids=ids)
-                self._exchange_bwd(nxt)
-                self._check_bwd()
-                eb = self._read_err()[S:S + self.b_hi].clone()
+                err, any_f, any_b = self._read_err_global()
+                ef = err[self.f_lo:S].clone()
+                eb = err[S:S + self.b_hi].clone()
+            any_f = any_b = repaired
             self.warm_cur, self.warm_valid = nxt, True
 
         c = self.core
