@@ -166,7 +166,7 @@ __global__ void emission_prepare_f16_kernel(int K, int N, const float* __restric
 // ---------------------------------------------------------------------------------------------
 struct EmissionTcParams {
   int64_t T;
-  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages, stagger, nostore, ep_nbuf;
+  int K, Kpad, BN, n_kblocks, n_mtiles, n_ntiles, stages, stagger, ep_nbuf;
   uint32_t idesc, tmem_cols;
   const float* lam_sum;
   const float* lgam;
@@ -340,7 +340,7 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int mp = unit / p.n_ntiles, nt = unit % p.n_ntiles;
       const int64_t t0 = (int64_t)(mp * EM_MI + mi) * TC_BM + q * 32;     // first row of this warp
       const float lg = (t0 + lane) < p.T ? __ldg(p.lgam + t0 + lane) : 0.f;
-      const bool rows_ok = t0 < p.T && !p.nostore;
+      const bool rows_ok = t0 < p.T;
       mbar_wait(tfull, (uint32_t)(it & 1));
       tc_fence_after();
 
@@ -627,16 +627,14 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   p.n_kblocks = (int)((ld16 + TC_BK - 1) / TC_BK);
   p.n_mtiles = (int)((T + TC_BM - 1) / TC_BM);
   p.n_ntiles = n_ntiles;
-  // experiment knobs (environment): PMG_EM_KERNEL=1 forces the single-tile kernel, PMG_EM_NOSTORE=1 drops the
-  // stores (timing only), PMG_EM_STAGES caps the pipeline depth, PMG_EM_STAGGER=0 disables the K-block rotation
+  // experiment knobs (environment): PMG_EM_KERNEL=1 forces the single-tile kernel, PMG_EM_STAGES caps the pipeline
+  // depth, PMG_EM_STAGGER=1 enables the per-CTA K-block rotation (changes the low bits of ll, see below)
   static const int kver_env = std::getenv("PMG_EM_KERNEL") ? std::atoi(std::getenv("PMG_EM_KERNEL")) : 2;
-  static const int nostore = std::getenv("PMG_EM_NOSTORE") ? std::atoi(std::getenv("PMG_EM_NOSTORE")) : 0;
   static const int st_env = std::getenv("PMG_EM_STAGES") ? std::atoi(std::getenv("PMG_EM_STAGES")) : 0;
   // default 0: every tile accumulates the neuron blocks in the same order, so ll[t,:] is bit-identical wherever
   // bin t sits in the launch -- time-sharded ranks recompute their neighbours' halo bins and their seam checks
   // compare messages at 1e-5 (a rotated order changes ll by ~3e-5 absolute, i.e. the likelihood by 3e-5 relative)
   static const int stagger_env = std::getenv("PMG_EM_STAGGER") ? std::atoi(std::getenv("PMG_EM_STAGGER")) : 0;
-  p.nostore = nostore;
   p.stagger = stagger_env;
   p.idesc = make_idesc_f16(TC_BM, BN, 0, 0, 0);
   p.tmem_cols = pow2_cols(2 * BN);

@@ -164,14 +164,11 @@ def emission_prepare_f16(tuning, y16, ma_neuron=None, dt=1.0):
         raise ValueError("y has %d neurons but tuning has %d" % (y16.N, N))
     bn = emission_tile_n(K)
     Kpad = (K + bn - 1) // bn * bn
-    brep = max(1, int(os.environ.get("PMG_EM_BREP", "1")))      # experiment: replicas of the operand
-    L16 = torch.empty((2 * brep, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
+    L16 = torch.empty((2, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
     lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
     check(lib.pmg_emission_prepare_f16(K, N, _p(tuning), _p(ma_neuron), float(dt), Kpad, y16.ld, _p(L16),
                                        _p(lam_sum), _stream()), "pmg_emission_prepare_f16")
     _count(1)
-    for r in range(1, brep):
-        L16[2 * r:2 * r + 2] = L16[:2]
     return L16, lam_sum
 
 

@@ -3,7 +3,7 @@ cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 r() { env "$@" timeout 120 python scripts/bench_emission.py 2>&1 | tail -1; }
 r TAG=v3
-r TAG=v3_nostore PMG_EM_NOSTORE=1
+
 r TAG=v3_st1 PMG_EM_STAGGER=0
 r TAG=v1 PMG_EM_KERNEL=1
 timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -k "emission or naive or atb or stat" > gpurun_out/pytest_h1.log 2>&1; echo "kernel tests rc=$?"
