@@ -150,3 +150,38 @@ def test_jax_random_documented_values():
     # odd sizes use the padded counter layout
     assert np.array_equal(jr.random_bits(key, 5)[:2], jr.random_bits(key, 5)[:2])
     assert jr.random_bits(key, 5).shape == (5,)
+
+
+def test_bench_reads_ncu_traffic_from_the_committed_profile():
+    """bench.py reports `roofline.traffic` from the committed ncu --set full summary: the file must exist,
+    parse, and carry the four hot kernels with plausible DRAM byte counts (headline workload)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    tr = bench.ncu_traffic()
+    for k in ("emission_tc_kernel", "atb_tc_kernel", "fwd_c_kernel", "bwd_c_kernel"):
+        assert k in tr, (k, sorted(tr))
+        assert 1e9 < tr[k] < 2e10
+    # emission moves its compulsory bytes (1 GB of fp16 counts in, 1.6 GB of ll out) and little more
+    assert 2.4e9 < tr["emission_tc_kernel"] < 3.0e9
+
+
+def test_clock_sampler_parses_nvidia_smi_lines():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _P:
+        def terminate(self): pass
+        def kill(self): pass
+        def communicate(self, timeout=None):
+            return ("2026/10/18 12:00:00.100, 1965, 1965, 700.1, Not Active, Not Active, Not Active, Active\n"
+                    "2026/10/18 12:00:00.200, 1800, 1965, 900.1, Not Active, Not Active, Not Active, Not Active\n"
+                    "garbage line\n", "")
+    s = bench.ClockSampler(0)
+    s.proc = _P()
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert abs(out["sm_mhz"] - 1882.5) < 1e-6
