@@ -136,6 +136,7 @@ class EMLoop:
         self._tuning = torch.empty((2, self.Phi.shape[0], model.n_neuron), dtype=torch.float32, device=self.W.device)
         self._tuning_i = 0
         self._spec = None                  # M-step result enqueued ahead for the next iteration (see iteration)
+        self.W_iter = self.W
         self._last_repaired = False
         # tensor-core statistics need fp16-exact counts; otherwise the fp32 CUDA-core tiles are used
         self.use_tc = self.es.y16 is not None and self.es.y16.exact
@@ -241,6 +242,8 @@ class EMLoop:
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16,
                           before_sync=enqueue_next if spec_ok else None)
         self._last_repaired = bool(res.repaired)
+        # GLM weights that produced THIS iteration's tuning (self.W may already hold the next M-step's result)
+        self.W_iter = nxt["snap"][0] if "m_res" in nxt else self.W
         if "m_res" in nxt:
             if res.repaired:
                 W, mu, nu, count, self._n_mstep, self._hist, self._tuning_i = nxt["snap"]
@@ -373,8 +376,9 @@ class PoissonGPLVMJump1D:
         pjm = hyperparam.get('p_jump_to_move', self.p_jump_to_move)
         # K x K host work (kernel matrices, band factorisation, stationary solve): a few ms, reused by repeated
         # fit / decode calls with the same dynamics
-        key = (float(mv), float(pmj), float(pjm), id(self.custom_transition_kernel), self.n_latent_bin,
-               str(self.device))
+        ck = self.custom_transition_kernel
+        ck_key = None if ck is None else hash(np.ascontiguousarray(np.asarray(ck, dtype=np.float32)).tobytes())
+        key = (float(mv), float(pmj), float(pjm), ck_key, self.n_latent_bin, str(self.device))
         cached = getattr(self, "_pack_cache", None)
         if cached is not None and cached[0] == key:
             return cached[1]
@@ -611,7 +615,7 @@ class PoissonGPLVMJump1D:
             estep_info.append((res.n_relay_fwd, res.n_relay_bwd, res.seam_err_fwd, res.seam_err_bwd))
             if snap:
                 saved['log_posterior_all_saved'].append(lazy_log(res.gamma))
-                saved['params_saved'].append(conv(W.clone()))
+                saved['params_saved'].append(conv(loop.W_iter.clone()))
                 saved['tuning_saved'].append(conv(tuning.clone() if return_device else tuning))
                 saved['log_marginal_saved'].append(res.log_marginal)
                 saved['iter_saved'].append(i)

@@ -145,6 +145,15 @@ def test_hyperparam_override_save_every_and_pickle():
     lw, lg = np.array(want["log_marginal_l"]), np.array(got["log_marginal_l"])
     assert np.max(np.abs(lg - lw) / np.abs(lw)) < 1e-4
     assert np.max(np.abs(np.exp(got["log_posterior_all_saved"][1]) - np.exp(want["log_posterior_all_saved"][1]))) < 5e-5
+    # every saved snapshot is self-consistent and matches the oracle's (the M-step of the NEXT iteration is
+    # enqueued ahead of time: the saved weights must be the ones that produced the saved tuning)
+    for j in range(2):
+        z = model.tuning_basis.astype(np.float64) @ got["params_saved"][j].astype(np.float64)
+        sp = np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
+        assert np.max(np.abs(sp - got["tuning_saved"][j]) / sp) < 1e-5
+        assert np.max(np.abs(got["params_saved"][j] - want["params_saved"][j])) < 1e-3
+        assert np.max(np.abs(got["tuning_saved"][j] - want["tuning_saved"][j]) / want["tuning_saved"][j]) < 1e-3
+    assert np.max(np.abs(got["params"] - want["params"])) < 1e-3
     m2 = pickle.loads(pickle.dumps(model))
     assert np.array_equal(m2.tuning, model.tuning) and m2.adam_runner is None
 
