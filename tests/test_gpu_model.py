@@ -151,9 +151,9 @@ def test_hyperparam_override_save_every_and_pickle():
         z = model.tuning_basis.astype(np.float64) @ got["params_saved"][j].astype(np.float64)
         sp = np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
         assert np.max(np.abs(sp - got["tuning_saved"][j]) / sp) < 1e-5
-        assert np.max(np.abs(got["params_saved"][j] - want["params_saved"][j])) < 1e-3
-        assert np.max(np.abs(got["tuning_saved"][j] - want["tuning_saved"][j]) / want["tuning_saved"][j]) < 1e-3
-    assert np.max(np.abs(got["params"] - want["params"])) < 1e-3
+        assert np.max(np.abs(got["params_saved"][j] - want["params_saved"][j])) < 3e-3
+        assert np.max(np.abs(got["tuning_saved"][j] - want["tuning_saved"][j]) / want["tuning_saved"][j]) < 3e-3
+    assert np.max(np.abs(got["params"] - want["params"])) < 3e-3
     m2 = pickle.loads(pickle.dumps(model))
     assert np.array_equal(m2.tuning, model.tuning) and m2.adam_runner is None
 
