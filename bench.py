@@ -263,7 +263,9 @@ def run_ours(args):
     model.params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
     P, logP, M, logM, op = model._transition_pack({})
     ma_n, ma_l = model._masks(None, None, T)
-    g = torch.Generator(device=dev); g.manual_seed(99)
+    # the reference's initial posterior is iid over ALL bins of the recording (core.py:571-583): every rank draws
+    # its own rows (rank 0 keeps the single-GPU stream)
+    g = torch.Generator(device=dev); g.manual_seed(99 + 7919 * rank)
     post0 = torch.rand((T, K), generator=g, device=dev)
     lp0 = torch.log(post0 / post0.sum(dim=1, keepdim=True))
     del post0

@@ -15,7 +15,7 @@ model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=10.0, movement_variance=
 model.params = np.random.default_rng(1).standard_normal((model.n_basis, N)).astype(np.float32)
 P, logP, M, logM, op = model._transition_pack({})
 ma_n, ma_l = model._masks(None, None, T)
-g = torch.Generator(device=dev); g.manual_seed(99)
+g = torch.Generator(device=dev); g.manual_seed(99 + 7919 * rank)
 post0 = torch.rand((T, K), generator=g, device=dev)
 lp0 = torch.log(post0 / post0.sum(dim=1, keepdim=True)); del post0
 loop = EMLoop(model, y, op, ma_n, ma_l, 1.0, model.tuning_basis, lp0, model.param_prior_std, 0.01, 1000, 1e-6, shard=TimeShard())
