@@ -1,0 +1,160 @@
+"""Host-side orchestration of the E-step on CPU: chain plan, warm starts carried from pass to pass, seam
+verification, Jacobi repair sweeps and the rank-boundary exchanges of `estep.EStep`, run under gloo with 1, 3
+and 8 ranks against the sequential (single-chain) answer of the linear-space oracle.
+
+The CUDA scan operators are replaced by NumPy stand-ins with the same interface conventions
+(tests/cpu_scan_emulation.py); everything else -- `EStep.run`, `TimeShard`, the plan -- is the product code.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _patch():
+    """Route the operators EStep uses to the CPU stand-ins; no CUDA call is left on its path."""
+    os.environ["PMG_SCAN_COMPACT"] = "0"
+    import cpu_scan_emulation as emu
+    from poor_man_gplvm_b200 import ops
+
+    class _Props:
+        multi_processor_count = 2
+
+    class _Stream:
+        def synchronize(self):
+            pass
+
+    torch.cuda.get_device_properties = lambda dev=None: _Props()
+    torch.cuda.current_stream = lambda dev=None: _Stream()
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    ops.forward, ops.backward, ops.seam_check = emu.forward, emu.backward, emu.seam_check
+    ops.EmissionOperands = emu.FakeEmission
+    ops.scan_compact_supported = lambda op, scale: False
+    return emu
+
+
+def _problem(T_total, N, K, seed):
+    from poor_man_gplvm_b200.synthetic import make_dataset
+    from poor_man_gplvm_b200 import gp_kernel as gpk
+    d = make_dataset(T_total, N, K, seed=seed)
+    P, logP, M, logM = gpk.create_transition_prob_1d(np.arange(K), np.arange(2), 1.0, 0.02, 0.05)
+    host = gpk.move_operator_host(K, 1.0, None, p_move_to_jump=0.02)
+    return d, P, M, host
+
+
+def _tunings(d, n_pass):
+    """A slowly changing tuning, as successive EM iterations produce (exercises the carried warm starts)."""
+    rng = np.random.default_rng(3)
+    base = d["tuning_true"].astype(np.float64)
+    out = []
+    for i in range(n_pass):
+        out.append((base * (1.0 + 0.05 * (n_pass - 1 - i) * rng.standard_normal(base.shape) * 0.2 + 0.0)).clip(1e-3))
+    return out
+
+
+def _worker(rank, world, port, cfg, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _patch()
+        from poor_man_gplvm_b200 import ops
+        from poor_man_gplvm_b200.estep import EStep
+        from poor_man_gplvm_b200.shard import TimeShard
+        T_total, N, K, halo, chunk, n_pass, seed = cfg
+        d, P, M, host = _problem(T_total, N, K, seed)
+        per = T_total // world
+        lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else T_total
+        y = torch.from_numpy(d["y"][lo:hi].copy())
+        op = ops.MoveOperator(host, M, torch.device("cpu"), P0=P[0])
+        es = EStep(y, op, None, None, 1.0, halo=halo, chunk_len=chunk, shard=TimeShard() if world > 1 else None)
+        out = []
+        for tun in _tunings(d, n_pass):
+            res = es.run(torch.from_numpy(tun.astype(np.float32)), want_gamma=True, want_gamma_lat=True,
+                         want_dyn=True, want_r=False)
+            lm = res.log_marginal.reshape(1).clone()
+            es.shard.allreduce_sum_(lm)
+            out.append({"gamma": res.gamma.numpy().copy(), "lm": float(lm[0]), "relay": (res.n_relay_fwd, res.n_relay_bwd),
+                        "repaired": res.repaired, "err": (res.seam_err_fwd, res.seam_err_bwd),
+                        "n_chain": res.plan.n_chain})
+        q.put((rank, out))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _run(world, cfg):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(world):
+        assert isinstance(res[r], list), res[r]
+    return res
+
+
+def _oracle(cfg):
+    from oracle import linear_ref as lin
+    T_total, N, K, halo, chunk, n_pass, seed = cfg
+    d, P, M, host = _problem(T_total, N, K, seed)
+    out = []
+    for tun in _tunings(d, n_pass):
+        r = lin.e_step(d["y"], tun, P.astype(np.float64), M.astype(np.float64), np.ones(N), np.ones(K))
+        # FakeEmission drops the lgamma row term (constant in k): same posteriors, shifted log marginal
+        from scipy.special import gammaln
+        out.append({"gamma": r["gamma"], "lm": r["log_marginal"] + gammaln(d["y"].astype(np.float64) + 1).sum()})
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_estep_orchestration_matches_sequential_answer(world):
+    # 8 ranks x 96 bins, chains of 24 bins, warm-up of 16: several chains per rank, rank boundaries with both
+    # neighbours, a warm-up too short for the first (cold) pass -> repair sweeps; later passes start warm
+    cfg = (768, 12, 24, 16, 24, 3, 5)
+    want = _oracle(cfg)
+    got = _run(world, cfg)
+    n_pass = cfg[5]
+    for i in range(n_pass):
+        gamma = np.concatenate([got[r][i]["gamma"] for r in range(world)])
+        assert gamma.shape == want[i]["gamma"].shape
+        assert np.max(np.abs(gamma - want[i]["gamma"])) < 2e-5
+        for r in range(world):
+            assert abs(got[r][i]["lm"] - want[i]["lm"]) < 1e-5 * abs(want[i]["lm"])
+            assert max(got[r][i]["err"]) <= 1e-5
+            # the verdict is global: every rank reports the same
+            assert got[r][i]["repaired"] == got[0][i]["repaired"]
+    assert got[0][0]["n_chain"] >= 2
+    # the cold first pass needs repairs somewhere (that path is the point of the test) ...
+    assert any(sum(got[r][0]["relay"]) > 0 for r in range(world))
+    # ... and warm starts carried across passes (and across rank boundaries) reduce them
+    first = sum(sum(got[r][0]["relay"]) for r in range(world))
+    last = sum(sum(got[r][n_pass - 1]["relay"]) for r in range(world))
+    assert last <= first
