@@ -199,3 +199,87 @@ class FakeEmission:
         ll = self.y.double() @ torch.log(lam).T - lam.sum(dim=1)[None, :]
         out.copy_(ll.float())
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# stand-ins for the operators of the EM loop (core.EMLoop): fp16 counts, fp16 posterior pieces, statistics
+# GEMM, Adam M-step (the oracle's restatement of the reference optimiser)
+# ---------------------------------------------------------------------------------------------------------
+class FakeCounts:
+    """Stands in for ops.CountsF16 (counts are small integers: exact)."""
+    exact = True
+
+    def __init__(self, y, ones_col=False, **kw):
+        self.T, self.N = y.shape
+        self.ones_col = bool(ones_col)
+        self.y = y
+
+
+class FakeEmissionTC(FakeEmission):
+    """Emission stand-in that also advertises the fp16 counts, so that EMLoop takes its tensor-core code path
+    (fp16 posterior pieces written by the backward pass, statistics from the pieces, speculation allowed)."""
+
+    def __init__(self, y, ma_neuron=None, impl=0, ones_col=False, dt_l=None):
+        super().__init__(y)
+        self.A16 = FakeCounts(y, ones_col=ones_col)
+
+
+def backward_with_pieces(plan, op, ll, alpha, gamma=None, gamma_lat=None, gamma16=None, **kw):
+    """backward() that also fills the fp16 hi/lo pieces of gamma_lat, as the CUDA kernels do."""
+    T, K = int(plan.T), op.K
+    gl = gamma_lat if gamma_lat is not None else torch.zeros((T, K), dtype=torch.float32)
+    if gamma16 is not None and kw.get("mode", 0) == 1:
+        gl.copy_(gamma16[0, :, :K].float() + gamma16[1, :, :K].float())     # rows of chains that are not re-run
+    backward(plan, op, ll, alpha, gamma=gamma, gamma_lat=gl, gamma16=None, **kw)
+    if gamma16 is not None:
+        for s, t_begin, t_end in _chains(plan, kw.get("mode", 0), kw.get("chain_ids")):
+            g = gl[t_begin:t_end]
+            hi = g.half()
+            gamma16[0, t_begin:t_end, :K] = hi
+            gamma16[1, t_begin:t_end, :K] = (g - hi.float()).half()
+
+
+def split_f16(src, out=None):
+    T, K = src.shape
+    if out is None:
+        out = torch.zeros((2, T, (K + 7) // 8 * 8), dtype=torch.float16)
+    hi = src.half()
+    out[0, :, :K] = hi
+    out[1, :, :K] = (src - hi.float()).half()
+    return out
+
+
+def atb_f16(g16, y16, K, out=None):
+    """[K, N (+1)] = sum_t gamma_lat[t,:K]^T [y | 1]."""
+    g = (g16[0, :, :K].double() + g16[1, :, :K].double())
+    Y = y16.y.double()
+    if y16.ones_col:
+        Y = torch.cat([Y, torch.ones((Y.shape[0], 1), dtype=torch.float64)], dim=1)
+    if g.shape[0] != Y.shape[0]:          # pieces cover the extended block; halo rows are zero
+        raise ValueError("row mismatch")
+    return (g.T @ Y).float()
+
+
+def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, tol=1e-6, min_iters=5,
+               b1=0.9, b2=0.999, eps=1e-8, out=None):
+    from oracle import ref_numpy as ref
+    opt = {"count": int(state.count.item()), "mu": state.mu.numpy().astype(np.float64),
+           "nu": state.nu.numpy().astype(np.float64)}
+    r = ref.adam_run(W.numpy().astype(np.float64), opt, float(prior_std), Phi.numpy().astype(np.float64),
+                     yw.numpy().astype(np.float64), tw.numpy().astype(np.float64), step_size, int(maxiter), tol,
+                     b1, b2, eps)
+    W.copy_(torch.from_numpy(r["params"].astype(np.float32)))
+    state.mu.copy_(torch.from_numpy(r["opt_state"]["mu"].astype(np.float32)))
+    state.nu.copy_(torch.from_numpy(r["opt_state"]["nu"].astype(np.float32)))
+    state.count.fill_(int(r["opt_state"]["count"]))
+    tuning_v = ref.get_tuning_softplus(r["params"], Phi.numpy().astype(np.float64)).astype(np.float32)
+    if out is None:
+        out = (torch.zeros(int(maxiter)), torch.zeros(int(maxiter)), torch.zeros(1, dtype=torch.int32),
+               torch.zeros(2), torch.zeros(tuning_v.shape))
+    lh, eh, ni, fin, tuning = out
+    lh.copy_(torch.from_numpy(r["loss_history"].astype(np.float32)))
+    eh.copy_(torch.from_numpy(r["error_history"].astype(np.float32)))
+    ni.fill_(int(r["n_iter"]))
+    fin.copy_(torch.tensor([float(r["final_loss"]), float(r["final_error"])]))
+    tuning.copy_(torch.from_numpy(tuning_v))
+    return lh, eh, ni, fin, tuning

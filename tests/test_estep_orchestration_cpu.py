@@ -158,3 +158,96 @@ def test_estep_orchestration_matches_sequential_answer(world):
     first = sum(sum(got[r][0]["relay"]) for r in range(world))
     last = sum(sum(got[r][n_pass - 1]["relay"]) for r in range(world))
     assert last <= first
+
+
+# ---------------------------------------------------------------------------------------------------------
+# EM loop (core.EMLoop): the M-step of the next iteration is enqueued ahead of the seam verdict and rolled back
+# when chains are re-run; time-sharded ranks broadcast the M-step result.  With deterministic stand-ins the
+# speculative loop must reproduce the plain loop bit for bit.
+# ---------------------------------------------------------------------------------------------------------
+def _em_worker(rank, world, port, cfg, speculate, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        emu = _patch()
+        import poor_man_gplvm_b200 as pmg
+        from poor_man_gplvm_b200 import ops
+        from poor_man_gplvm_b200.core import EMLoop
+        from poor_man_gplvm_b200.shard import TimeShard
+        ops.EmissionOperands = emu.FakeEmissionTC
+        ops.backward, ops.atb_f16, ops.split_f16, ops.mstep_adam = (emu.backward_with_pieces, emu.atb_f16,
+                                                                    emu.split_f16, emu.mstep_adam)
+        T_total, N, K, halo, chunk, n_iter, seed = cfg
+        d, P, M, host = _problem(T_total, N, K, seed)
+        per = T_total // world
+        lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else T_total
+        cpu = torch.device("cpu")
+        model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=6.0, device=cpu)
+        rng = np.random.default_rng(11)
+        model.params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
+        post0 = rng.random((T_total, K)) + 0.05
+        lp0 = np.log(post0 / post0.sum(axis=1, keepdims=True)).astype(np.float32)
+        op = ops.MoveOperator(host, M, cpu, P0=P[0])
+        ma_n, ma_l = model._masks(None, None, hi - lo)
+        loop = EMLoop(model, torch.from_numpy(d["y"][lo:hi].copy()), op, ma_n, ma_l, 1.0, model.tuning_basis,
+                      lp0[lo:hi], 1.0, 0.01, 15, -1.0, halo=halo, chunk_len=chunk,
+                      shard=TimeShard() if world > 1 else None)
+        assert loop.use_tc
+        out = []
+        for i in range(n_iter):
+            res, m_res = loop.iteration(speculate=(speculate and i < n_iter - 1))
+            out.append({"tuning": m_res[4].numpy().copy(), "W_iter": loop.W_iter.numpy().copy(),
+                        "n_adam": int(m_res[2].item()), "lm": float(res.log_marginal),
+                        "repaired": bool(res.repaired), "relay": (res.n_relay_fwd, res.n_relay_bwd)})
+        out.append({"W": loop.W.numpy().copy(), "count": int(loop.state.count.item()),
+                    "Phi": loop.Phi.numpy().copy()})
+        q.put((rank, out))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _run_em(world, cfg, speculate):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_em_worker, args=(r, world, port, cfg, speculate, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=900) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(world):
+        assert isinstance(res[r], list), res[r]
+    return res
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_em_loop_speculative_mstep_equals_plain_loop(world):
+    cfg = (288, 12, 24, 16, 24, 5, 5)
+    plain = _run_em(world, cfg, speculate=False)
+    spec = _run_em(world, cfg, speculate=True)
+    n_iter = cfg[5]
+    for r in range(world):
+        for i in range(n_iter):
+            a, b = plain[r][i], spec[r][i]
+            assert np.array_equal(a["tuning"], b["tuning"]), (r, i)
+            assert np.array_equal(a["W_iter"], b["W_iter"]), (r, i)
+            assert a["n_adam"] == b["n_adam"] == 15 and a["lm"] == b["lm"]
+            assert a["repaired"] == b["repaired"] and a["relay"] == b["relay"]
+            # the reported weights are the ones that produced the reported tuning
+            z = plain[r][-1]["Phi"].astype(np.float64) @ b["W_iter"].astype(np.float64)
+            sp = np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
+            assert np.max(np.abs(sp - b["tuning"]) / sp) < 1e-5
+        assert np.array_equal(plain[r][-1]["W"], spec[r][-1]["W"])
+        assert plain[r][-1]["count"] == spec[r][-1]["count"] == 14 * n_iter
+        # replicated M-step: identical on every rank
+        assert np.array_equal(spec[r][n_iter - 1]["tuning"], spec[0][n_iter - 1]["tuning"])
+    # the scenario must contain at least one repaired iteration (rollback path) and one clean one
+    rep = [spec[0][i]["repaired"] for i in range(n_iter)]
+    assert any(rep)
