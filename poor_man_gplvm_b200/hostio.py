@@ -153,7 +153,7 @@ def to_numpy(t, out=None):
     if not isinstance(t, torch.Tensor):
         return np.asarray(t)
     if not t.is_cuda:
-        return t.detach().numpy()
+        return t.detach().numpy().copy()          # always a fresh array, like the device path
     t = t.detach().contiguous()
     nbytes = t.numel() * t.element_size()
     if nbytes < (8 << 20):

@@ -251,3 +251,71 @@ def test_em_loop_speculative_mstep_equals_plain_loop(world):
     # the scenario must contain at least one repaired iteration (rollback path) and one clean one
     rep = [spec[0][i]["repaired"] for i in range(n_iter)]
     assert any(rep)
+
+
+def _fit_worker(q):
+    try:
+        emu = _patch()
+        import poor_man_gplvm_b200 as pmg
+        from poor_man_gplvm_b200 import ops
+        from oracle import ref_numpy as ref
+        from poor_man_gplvm_b200.synthetic import make_dataset
+        ops.EmissionOperands = emu.FakeEmissionTC
+        ops.backward, ops.atb_f16, ops.split_f16, ops.mstep_adam = (emu.backward_with_pieces, emu.atb_f16,
+                                                                    emu.split_f16, emu.mstep_adam)
+        os.environ["PMG_HALO"] = "16"
+        N, K, T = 10, 24, 160
+        d = make_dataset(T, N, K, seed=9)
+        cpu = torch.device("cpu")
+        model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=6.0, device=cpu)
+        rng = np.random.default_rng(2)
+        params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
+        model.params = params.copy()
+        oracle = ref.OraclePoissonGPLVMJump1D(N, K, tuning_lengthscale=6.0, dtype=np.float64,
+                                              tuning_basis=model.tuning_basis, params=params)
+        post0 = rng.random((T, K)) + 0.05
+        lp0 = np.log(post0 / post0.sum(axis=1, keepdims=True)).astype(np.float32)
+        kw = dict(n_iter=4, log_posterior_init=lp0, m_step_maxiter=12, m_step_tol=-1, save_every=2)
+        want = oracle.fit_em(d["y"], **kw)
+        got = model.fit_em(d["y"], **kw)
+        out = {"iter_saved": got["iter_saved"],
+               "params_saved": [np.asarray(a) for a in got["params_saved"]],
+               "tuning_saved": [np.asarray(a) for a in got["tuning_saved"]],
+               "params": np.asarray(got["params"]), "tuning": np.asarray(got["tuning"]),
+               "post": np.asarray(got["posterior_latent_marg"]), "dyn": np.asarray(got["posterior_dynamics_marg"]),
+               "lml": np.array(got["log_marginal_l"], dtype=np.float64),
+               "n_adam": list(got["m_step_res_l"]["n_iter"]),
+               "w_params_saved": want["params_saved"], "w_tuning_saved": want["tuning_saved"],
+               "w_params": want["params"], "w_post": want["posterior_latent_marg"],
+               "w_dyn": want["posterior_dynamics_marg"], "w_lml": np.array(want["log_marginal_l"]),
+               "y": d["y"], "basis": model.tuning_basis}
+        q.put(out)
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put(traceback.format_exc())
+
+
+def test_fit_em_control_flow_on_cpu_matches_oracle():
+    """fit_em end to end (snapshots, speculative M-steps, last iteration with full outputs, result dictionary)
+    with the CPU stand-ins, against the oracle's fit_em."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_fit_worker, args=(q,))
+    p.start()
+    out = q.get(timeout=900)
+    p.join(timeout=60)
+    assert isinstance(out, dict), out
+    assert out["iter_saved"] == [0, 2] and out["n_adam"] == [12] * 4
+    for j in range(2):
+        assert np.max(np.abs(out["params_saved"][j] - out["w_params_saved"][j])) < 1e-4
+        assert np.max(np.abs(out["tuning_saved"][j] - out["w_tuning_saved"][j]) / out["w_tuning_saved"][j]) < 1e-4
+        z = out["basis"].astype(np.float64) @ out["params_saved"][j].astype(np.float64)
+        sp = np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
+        assert np.max(np.abs(sp - out["tuning_saved"][j]) / sp) < 1e-5
+    assert np.max(np.abs(out["params"] - out["w_params"])) < 1e-4
+    assert np.max(np.abs(out["post"] - out["w_post"])) < 2e-5
+    assert np.max(np.abs(out["dyn"] - out["w_dyn"])) < 2e-5
+    # FakeEmission drops the lgamma row term: constant shift of every log marginal
+    from scipy.special import gammaln
+    shift = gammaln(out["y"].astype(np.float64) + 1).sum()
+    assert np.max(np.abs(out["lml"] - shift - out["w_lml"]) / np.abs(out["w_lml"])) < 1e-5
