@@ -38,6 +38,22 @@ def check_fwd(compact=False):
                float(a[es.K:].sum()), float(b[es.K:].sum())), flush=True)
 es._check_fwd = check_fwd
 from poor_man_gplvm_b200 import ops as _ops
+if os.environ.get("DUMP_SEAMS"):
+    # first verdict of every E-step (before any repair): which seams are over the tolerance, and by how much
+    _orig_verdict = es._read_err_global
+    _calls = {"n": 0}
+    def _verdict():
+        out = _orig_verdict()
+        err, any_f, any_b = out
+        ef = err[es.f_lo:es.S].clone(); eb = err[es.S:es.S + es.b_hi].clone()
+        bf = torch.nonzero(ef > es.seam_tol).flatten(); bb = torch.nonzero(eb > es.seam_tol).flatten()
+        _calls["n"] += 1
+        if bf.numel() or bb.numel():
+            print("  [rank %d verdict %d] fwd over tol: %s | bwd over tol: %s | S=%d" %
+                  (rank, _calls["n"], [(int(i) + es.f_lo, "%.2e" % float(ef[i])) for i in bf[:6]],
+                   [(int(i), "%.2e" % float(eb[i])) for i in bb[:6]], es.S), flush=True)
+        return out
+    es._read_err_global = _verdict
 marks = []
 if os.environ.get("HOSTMARKS"):
     _ops.PHASE_HOOK = lambda name: marks.append((name, time.perf_counter()))
