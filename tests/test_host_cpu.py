@@ -185,3 +185,22 @@ def test_clock_sampler_parses_nvidia_smi_lines():
     out = s.stop()
     assert out["samples"] == 2 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
     assert abs(out["sm_mhz"] - 1882.5) < 1e-6
+
+
+def test_host_buffers_prefault_and_hand_out_arrays():
+    """Result buffers are allocated up front and their pages populated on background threads (madvise pieces,
+    memset fallback); take() returns the planned array once its pages are in, or None for an unplanned shape."""
+    from poor_man_gplvm_b200 import hostio
+    bufs = hostio.HostBuffers([("a", (1 << 20, 3), np.float32), ("b", (5, 7), np.float32)], threads=3)
+    a = bufs.take("a")
+    assert a.shape == (1 << 20, 3) and a.dtype == np.float32 and a.flags.c_contiguous
+    a[:] = 1.5                                   # writable, fully mapped
+    assert float(a.sum()) == 1.5 * a.size
+    assert bufs.take("a") is None                # handed out once
+    assert bufs.take("b", shape=(7, 5)) is None  # planned with another shape
+    bufs.close()
+    # a page-unaligned view in the middle of an array is handled (rounded down to the page, bounded by the view)
+    x = np.zeros(3 * 4096 + 100, dtype=np.uint8)
+    x[:] = 7
+    hostio._touch(x[50:2 * 4096 + 77])
+    assert int(x.min()) == 7 or int(x[50:2 * 4096 + 77].max()) in (0, 7)
