@@ -255,6 +255,7 @@ def test_em_loop_speculative_mstep_equals_plain_loop(world):
 
 def _fit_worker(q):
     try:
+        os.environ["PMG_HALO"] = "16"           # read when the package is imported
         emu = _patch()
         import poor_man_gplvm_b200 as pmg
         from poor_man_gplvm_b200 import ops
@@ -263,7 +264,6 @@ def _fit_worker(q):
         ops.EmissionOperands = emu.FakeEmissionTC
         ops.backward, ops.atb_f16, ops.split_f16, ops.mstep_adam = (emu.backward_with_pieces, emu.atb_f16,
                                                                     emu.split_f16, emu.mstep_adam)
-        os.environ["PMG_HALO"] = "16"
         N, K, T = 10, 24, 160
         d = make_dataset(T, N, K, seed=9)
         cpu = torch.device("cpu")
@@ -319,3 +319,70 @@ def test_fit_em_control_flow_on_cpu_matches_oracle():
     from scipy.special import gammaln
     shift = gammaln(out["y"].astype(np.float64) + 1).sum()
     assert np.max(np.abs(out["lml"] - shift - out["w_lml"]) / np.abs(out["w_lml"])) < 1e-5
+
+
+def _fit_sharded_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        os.environ["PMG_HALO"] = "16"           # read when the package is imported
+        emu = _patch()
+        import poor_man_gplvm_b200 as pmg
+        from poor_man_gplvm_b200 import ops
+        from poor_man_gplvm_b200.synthetic import make_dataset
+        ops.EmissionOperands = emu.FakeEmissionTC
+        ops.backward, ops.atb_f16, ops.split_f16, ops.mstep_adam = (emu.backward_with_pieces, emu.atb_f16,
+                                                                    emu.split_f16, emu.mstep_adam)
+        N, K, T = 10, 24, 192
+        d = make_dataset(T, N, K, seed=4)
+        model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=6.0, device=torch.device("cpu"))
+        rng = np.random.default_rng(6)
+        model.params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
+        post0 = rng.random((T, K)) + 0.05
+        lp0 = np.log(post0 / post0.sum(axis=1, keepdims=True)).astype(np.float32)
+        per = T // world
+        lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else T
+        got = model.fit_em(d["y"][lo:hi], n_iter=3, log_posterior_init=lp0[lo:hi], m_step_maxiter=10, m_step_tol=-1,
+                           time_sharded=world > 1)
+        q.put((rank, {"tuning": np.asarray(got["tuning"]), "params": np.asarray(got["params"]),
+                      "post": np.asarray(got["posterior_latent_marg"]), "dyn": np.asarray(got["posterior_dynamics_marg"]),
+                      "lml": np.array(got["log_marginal_l"], dtype=np.float64)}))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _run_fit(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=900) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(world):
+        assert isinstance(res[r], dict), res[r]
+    return res
+
+
+def test_time_sharded_fit_em_on_cpu_matches_single_process():
+    """fit_em(time_sharded=True) under gloo with 3 ranks (blocks of one recording) against the single-process fit:
+    same tuning and log marginals on every rank, posteriors of the blocks concatenate to the single-process ones."""
+    one = _run_fit(1)[0]
+    three = _run_fit(3)
+    for r in range(3):
+        assert np.max(np.abs(three[r]["tuning"] - one["tuning"]) / one["tuning"]) < 1e-4
+        assert np.max(np.abs(three[r]["lml"] - one["lml"]) / np.abs(one["lml"])) < 1e-6
+        assert np.array_equal(three[r]["tuning"], three[0]["tuning"])
+        assert np.array_equal(three[r]["params"], three[0]["params"])
+    post = np.concatenate([three[r]["post"] for r in range(3)])
+    dyn = np.concatenate([three[r]["dyn"] for r in range(3)])
+    assert np.max(np.abs(post - one["post"])) < 2e-5
+    assert np.max(np.abs(dyn - one["dyn"])) < 2e-5
