@@ -123,11 +123,17 @@ typedef struct pmg_scan_plan {
   int left_exact;     /* bin 0 is the true start of the sequence (or carry_in is exact) */
   int right_exact;    /* bin T-1 is the true end of the sequence (or beta_in is exact) */
   float likelihood_scale;
+  int halo_next;      /* warm-up length of the NEXT pass (where warm_out messages are taken); 0 = halo */
+  float sel_tol;      /* mode 2: chain s is re-run iff !(sel_err[s] <= sel_tol) */
+  const float* sel_err; /* mode 2: device array [n_chain] of seam errors (pmg_seam_check_fix) */
 } pmg_scan_plan;
 
 /* mode 0: all chains, warm-up from the uniform carry (left-most chain exact if left_exact).
  * mode 1: relay — run only chains listed in chain_ids[n_ids] (device int32) starting
  *         from the exact carry alpha[t_begin-1].
+ * mode 2: like mode 1 with the selection made on the device: every chain s with !(plan->sel_err[s] <=
+ *         plan->sel_tol) restarts from its snapshot (warm_in), the others return at once.  Together with
+ *         pmg_seam_check_fix this repairs failed seams without a host round trip.
  * alpha:   [T, 2, K] (ld = 2*ldk), lmr: [T] = log c_t + s*max_k ll[t,k]
  * carry_in: [2,K] or NULL (uniform);   halo_state: [n_chain, 2, K] warmed-up state at t_begin-1.
  * warm_in:  message a warm-up starts from: one [2,K] vector (warm_stride 0, e.g. the stationary
@@ -160,6 +166,10 @@ int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const floa
  * renormalises).  est/truth are [n, len] with row strides in elements (truth rows may live inside alpha). */
 int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, const float* truth,
                    int64_t ld_truth, float floor_val, float* err, pmg_stream_t stream);
+/* Same check; seams with !(err <= tol) add 1 to *counter (device float, may be NULL) and, with fix != 0, have
+ * their estimate row overwritten by the truth row -- the snapshot a mode-2 restart of that chain starts from. */
+int pmg_seam_check_fix(int n, int len, float* est, int64_t ld_est, const float* truth, int64_t ld_truth,
+                       float floor_val, float tol, int fix, float* err, float* counter, pmg_stream_t stream);
 /* EM-iteration fast path of the two passes ("compact" filtered posterior).  The filtered jump-state
  * message is a scalar multiple of the likelihood factor, alpha_t[1,x] = a1s_t * exp2(s*log2e*(ll[t,x] -
  * max_x ll[t,:])), so the forward pass stores ax[T, ldax] with columns 0..K-1 = alpha_t[0,:], column K =
@@ -231,6 +241,14 @@ int pmg_mstep_adam(int K, int B, int N, const float* Phi, const float* yw, const
                    int min_iters, float* W, float* mu, float* nu, int* count, float* loss_hist,
                    float* err_hist, int* n_iter_out, float* final_out, float* tuning_out,
                    void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
+
+/* Same with strided statistics: yw[k,n] at yw[k*ldyw + n], tw[k] at tw[k*tw_stride] -- the [K, N+1] output of
+ * pmg_atb_f16 on counts with a ones column is consumed in place (yw = out, ldyw = N+1, tw = out + N, stride N+1). */
+int pmg_mstep_adam_ld(int K, int B, int N, const float* Phi, const float* yw, int64_t ldyw, const float* tw,
+                      int64_t tw_stride, float prior_std, float lr, float b1, float b2, float eps, int maxiter,
+                      float tol, int min_iters, float* W, float* mu, float* nu, int* count, float* loss_hist,
+                      float* err_hist, int* n_iter_out, float* final_out, float* tuning_out,
+                      void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
 
 /* tuning[k,n] = softplus(sum_b Phi[k,b]*W[b,n])   (fit_tuning_helper.py:11-25) */
 int pmg_tuning_softplus(int K, int B, int N, const float* Phi, const float* W, float* tuning,

@@ -96,3 +96,42 @@ def e_step(y, tuning, P, M, ma_neuron, ma_latent, likelihood_scale=1.0, dtype=np
     else:
         res["gamma"] = out
     return res
+
+
+def fit_em_linear(model, y, hyperparam={}, n_iter=20, log_posterior_init=None, ma_neuron=None, ma_latent=None,
+                  likelihood_scale=1.0, m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6):
+    """The reference EM driver (core.py:592-713, :802-849) with the restated M-step of ``ref_numpy`` and the
+    E-step in linear space (``e_step`` above) instead of the per-step log-space joint.  The log-space restatement
+    costs 4K^2 exponentials per bin; this one two K x K mat-vecs, which is what makes parity runs at the real
+    shapes (K=400 / K=2000, thousands of bins) affordable.  ``model``: an ``OraclePoissonGPLVMJump1D`` in
+    fp64.  PINNED through ``tests/test_oracle_golden.py::test_linear_em_driver_matches_reference_source``: it
+    reproduces the reference source's README run (golden fixture) to 1e-9."""
+    from . import ref_numpy as ref
+    fd = np.float64
+    y_ = np.asarray(y, dtype=fd)
+    hp = dict(hyperparam)
+    prior_std = hp.get("param_prior_std", model.param_prior_std)
+    P, _, M, _ = model._transitions(hp)
+    P = np.asarray(P, dtype=fd); M = np.asarray(M, dtype=fd)
+    ma_neuron = model.ma_neuron_default if ma_neuron is None else np.asarray(ma_neuron, dtype=fd)
+    ma_latent = model.ma_latent_default if ma_latent is None else np.asarray(ma_latent, dtype=fd)
+    basis = np.asarray(model.tuning_basis, dtype=fd)
+    params = np.asarray(model.params, dtype=fd)
+    lp_curr = np.asarray(log_posterior_init, dtype=fd)
+    opt_state = ref.adam_init(params)
+    lml_l, n_it, losses = [], [], []
+    for _ in range(n_iter):
+        yw, tw = ref.get_statistics(lp_curr, y_)
+        m_res = ref.adam_run(params, opt_state, prior_std, basis, yw, tw, step_size=m_step_step_size,
+                             maxiter=m_step_maxiter, tol=m_step_tol)
+        params, opt_state = m_res["params"], m_res["opt_state"]
+        n_it.append(int(m_res["n_iter"])); losses.append(float(m_res["final_loss"]))
+        tuning = ref.get_tuning_softplus(params, basis)
+        es = e_step(y_, tuning, P, M, ma_neuron, ma_latent, likelihood_scale, dtype=fd)
+        gamma = es["gamma"]
+        with np.errstate(divide="ignore"):
+            lp_curr = np.log(gamma.sum(axis=1))
+        lml_l.append(float(es["log_marginal"]))
+    return {"params": params, "tuning": tuning, "log_marginal_l": lml_l, "posterior": gamma,
+            "posterior_latent_marg": gamma.sum(axis=1), "posterior_dynamics_marg": gamma.sum(axis=2),
+            "m_step_n_iter": n_it, "m_step_final_loss": losses, "alpha": es["alpha"], "ll": es["ll"]}

@@ -27,7 +27,8 @@ class PmgScanPlan(C.Structure):
     _fields_ = [("T", C.c_int64), ("core_begin", C.c_int64), ("core_end", C.c_int64),
                 ("chunk_len", C.c_int64), ("n_chain", C.c_int), ("halo", C.c_int),
                 ("left_exact", C.c_int), ("right_exact", C.c_int),
-                ("likelihood_scale", C.c_float)]
+                ("likelihood_scale", C.c_float), ("halo_next", C.c_int), ("sel_tol", C.c_float),
+                ("sel_err", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/pmgplvm_b200.h
@@ -74,6 +75,8 @@ SIGNATURES = {
                               C.c_void_p, C.c_int64, c_stream]),
     "pmg_seam_check": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_float, c_f32p,
                                  c_stream]),
+    "pmg_seam_check_fix": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_float, C.c_float,
+                                     C.c_int, c_f32p, c_f32p, c_stream]),
     "pmg_atb_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "pmg_atb": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64,
                           C.c_void_p, C.c_int64, C.c_int, c_stream]),
@@ -83,6 +86,10 @@ SIGNATURES = {
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, c_f32p, c_f32p,
                                  c_f32p, c_i32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, C.c_void_p, C.c_int64,
                                  c_stream]),
+    "pmg_mstep_adam_ld": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_int64,
+                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
+                                    C.c_int, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p,
+                                    C.c_void_p, C.c_int64, c_stream]),
     "pmg_threefry_posterior_init": (C.c_int, [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
                                               C.c_float, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_void_p, C.c_int64,
                                               C.c_int64, C.c_void_p, c_stream]),

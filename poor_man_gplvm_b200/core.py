@@ -20,6 +20,7 @@ from . import gp_kernel as gpk
 from . import hostio
 from . import jaxprng
 from . import ops
+from . import estep
 from .estep import EStep
 from .shard import TimeShard
 
@@ -127,9 +128,15 @@ class EMLoop:
         if self.W.shape != (self.Phi.shape[1], model.n_neuron):
             raise ValueError("params shape %s does not match basis %s" % (tuple(self.W.shape), tuple(self.Phi.shape)))
         self.state = ops.AdamState(self.W)
+        # One buffer holds everything an EM iteration sums over ranks: the statistics [K, N+1] (column N =
+        # sum_t gamma) followed by the E-step's record (log marginal, seam verdict) -> ONE all-reduce per iteration
+        K_, N1 = op.K, model.n_neuron + 1
+        self.pack = torch.zeros(K_ * N1 + estep.TAIL, dtype=torch.float32, device=self.W.device)
+        self.stats = self.pack[:K_ * N1].view(K_, N1)
         self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len, shard=shard,
-                        em_mode=True)
+                        em_mode=True, tail=self.pack[K_ * N1:])
         self.shard = self.es.shard
+        self.broadcast_mstep = os.environ.get("PMG_MSTEP_BROADCAST", "0") != "0"
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
         self._n_mstep = 0
         self._hist = self._new_hist_block()
@@ -182,24 +189,26 @@ class EMLoop:
         return (torch.empty((n, mi), dtype=torch.float32, device=dev), torch.empty((n, mi), dtype=torch.float32, device=dev),
                 torch.empty(n, dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.float32, device=dev))
 
-    def _stats_and_mstep(self):
-        """Sufficient statistics of the current posterior + the Adam M-step (reference core.py:807-810)."""
+    def _stats_and_mstep(self, with_record=False):
+        """Sufficient statistics of the current posterior + the Adam M-step (reference core.py:807-810).
+        with_record: the E-step's record behind the statistics is final and travels in the same all-reduce."""
+        N = self.stats.shape[1] - 1
         if self.use_tc:
             # reference core.py:807; the ones column of the fp16 counts makes column N = sum_t gamma
-            stats = ops.atb_f16(self.gamma16, self.es.y16, self.es.K)
-            N = self.es.y16.N
-            yw, self.tw = stats[:, :N].contiguous(), stats[:, N].contiguous()
+            ops.atb_f16(self.gamma16, self.es.y16, self.es.K, out=self.stats)
         else:
-            yw = ops.atb(self.gamma_lat, self.y)
-        self.shard.allreduce_sum_(yw, self.tw)                      # time-sharded ranks: one packed all-reduce
+            ops.atb(self.gamma_lat, self.y, out=self.stats[:, :N])
+            self.stats[:, N] = self.tw
+        # time-sharded ranks: one all-reduce (fp32 on the wire, in place, no packing copies)
+        self.shard.allreduce_flat_sum_(self.pack if with_record else self.pack[:self.stats.numel()])
         ops.phase("stats")
-        m_res = ops.mstep_adam(self.Phi, yw, self.tw, self.W, self.state, self.prior_std, self.step_size,
-                               self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
-        if self.shard.active:
-            # The M-step is replicated.  Every rank must use the same tuning bit for bit (ranks recompute their
-            # neighbours' halo bins and verify boundary seams at 1e-5) and keep the same optimiser state, so
-            # rank 0's result is broadcast: 1.2 MB, one collective, instead of relying on every rank's inputs
-            # and arithmetic being bit-identical.
+        m_res = ops.mstep_adam(self.Phi, self.stats[:, :N], self.stats[:, N], self.W, self.state, self.prior_std,
+                               self.step_size, self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
+        if self.shard.active and self.broadcast_mstep:
+            # The M-step is replicated: every rank runs the same deterministic kernel on the bit-identical result
+            # of the all-reduce, so tuning and optimiser state agree bit for bit without communication (ranks
+            # recompute their neighbours' halo bins and verify boundary seams at 1e-5; a divergence would show up
+            # there).  PMG_MSTEP_BROADCAST=1 restores the explicit broadcast of rank 0's result (debugging).
             st = self.state
             parts = [m_res[4], self.W, st.mu, st.nu]
             flat = torch.cat([t.reshape(-1) for t in parts] + [st.count.to(torch.float32)])
@@ -236,7 +245,7 @@ class EMLoop:
             st = self.state
             nxt["snap"] = (self.W.clone(), st.mu.clone(), st.nu.clone(), st.count.clone(), self._n_mstep,
                            self._hist, self._tuning_i)
-            nxt["m_res"] = self._stats_and_mstep()
+            nxt["m_res"] = self._stats_and_mstep(with_record=True)
 
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16,
@@ -253,11 +262,7 @@ class EMLoop:
         self.gamma_lat = res.gamma_lat                             # reference core.py:668
         if res.tw is not None:
             self.tw = res.tw
-        if self.shard.active:
-            lm = res.log_marginal.reshape(1)
-            self.shard.allreduce_sum_(lm)
-            res.log_marginal = lm[0]
-        return res, m_res
+        return res, m_res                                          # res.log_marginal is global already
 
 
 class PoissonGPLVMJump1D:
@@ -457,10 +462,6 @@ class PoissonGPLVMJump1D:
         es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, shard=TimeShard(group) if time_sharded else None)
         res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=True, want_dyn=True,
                      want_r=(T > 1 or es.shard.active))
-        if es.shard.active:
-            lm = res.log_marginal.reshape(1)
-            es.shard.allreduce_sum_(lm)
-            res.log_marginal = lm[0]
         conv = (lambda t: t) if return_device else self._host
         # the reference leaves these on the device as jax arrays (core.py:489, decoder.py:360-375)
         lazy = (lambda t: t) if return_device else hostio.LazyHostArray
@@ -638,7 +639,8 @@ class PoissonGPLVMJump1D:
         self.log_dynamics_transition_kernel = logM
         self.tuning_basis = tuning_basis
         self._last_estep_info = {"n_chain": es.plan.n_chain, "chunk_len": es.chunk_len, "halo": es.halo,
-                                 "per_iter": estep_info}
+                                 "per_iter": estep_info, "tensor_core_statistics": bool(loop.use_tc),
+                                 "compact_scan": bool(es.compact_ok and loop.use_tc)}
         self._opt_state = state
 
         em_res = dict(saved)

@@ -22,8 +22,9 @@ constexpr int MS_THREADS = 256;
 struct MstepParams {
   int K, B, N;
   const float* Phi;
-  const float* yw;
-  const float* tw;
+  const float* yw;       // [K, ldyw]
+  const float* tw;       // element k at tw[k * tws]
+  int64_t ldyw, tws;
   float prior_std, lr, b1, b2, eps;
   int maxiter;
   float tol;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mstep_adam_kernel(const MstepPa
           z[0] = fmaf(ph, w4.x, z[0]); z[1] = fmaf(ph, w4.y, z[1]);
           z[2] = fmaf(ph, w4.z, z[2]); z[3] = fmaf(ph, w4.w, z[3]);
         }
-        const float twk = p.tw[k];
+        const float twk = p.tw[(size_t)k * p.tws];
 #pragma unroll
         for (int nt = 0; nt < MS_NT; ++nt) {
           float e = 0.f;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mstep_adam_kernel(const MstepPa
             if (write_tuning) {
               p.tuning_out[(size_t)k * N + n0 + nt] = pf;
             } else {
-              const float ywv = p.yw[(size_t)k * N + n0 + nt];
+              const float ywv = p.yw[(size_t)k * p.ldyw + n0 + nt];
               const float pfe = pf + kLamFloor;
               e = (ywv / pfe - twk) * sigmoid_f(z[nt]);
               const float fit = (ywv == 0.f) ? 0.f : ywv * logf(pfe);
@@ -288,9 +289,9 @@ __global__ void __launch_bounds__(LT, 1) mstep_adam_lag_kernel(const MstepParams
   }
   for (int i = tid; i < K * MS_NT; i += LT) {
     const int k = i / MS_NT, nt = i % MS_NT;
-    ywS[i] = (n0 + nt < N) ? p.yw[(size_t)k * N + n0 + nt] : 0.f;
+    ywS[i] = (n0 + nt < N) ? p.yw[(size_t)k * p.ldyw + n0 + nt] : 0.f;
   }
-  for (int k = tid; k < K; k += LT) twS[k] = p.tw[k];
+  for (int k = tid; k < K; k += LT) twS[k] = p.tw[(size_t)k * p.tws];
   __syncthreads();
   const float* phi = p.phi_in_smem ? phiS : p.Phi;
   const int ldphi = p.phi_in_smem ? Bs : B;
@@ -517,15 +518,26 @@ extern "C" int pmg_mstep_adam(int K, int B, int N, const float* Phi, const float
                               int min_iters, float* W, float* mu, float* nu, int* count, float* loss_hist,
                               float* err_hist, int* n_iter_out, float* final_out, float* tuning_out,
                               void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
+  return pmg_mstep_adam_ld(K, B, N, Phi, yw, N, tw, 1, prior_std, lr, b1, b2, eps, maxiter, tol, min_iters, W, mu, nu,
+                           count, loss_hist, err_hist, n_iter_out, final_out, tuning_out, workspace, workspace_bytes,
+                           stream);
+}
+
+extern "C" int pmg_mstep_adam_ld(int K, int B, int N, const float* Phi, const float* yw, int64_t ldyw,
+                                 const float* tw, int64_t tw_stride,
+                                 float prior_std, float lr, float b1, float b2, float eps, int maxiter, float tol,
+                                 int min_iters, float* W, float* mu, float* nu, int* count, float* loss_hist,
+                                 float* err_hist, int* n_iter_out, float* final_out, float* tuning_out,
+                                 void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
   using namespace pmg;
-  if (K <= 0 || B <= 0 || N <= 0 || maxiter < 1) return PMG_ERR_BAD_ARG;
+  if (K <= 0 || B <= 0 || N <= 0 || maxiter < 1 || ldyw < N || tw_stride < 1) return PMG_ERR_BAD_ARG;
   if (!Phi || !yw || !tw || !W || !mu || !nu || !count || !loss_hist || !err_hist || !n_iter_out || !final_out)
     return PMG_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < pmg_mstep_workspace_bytes(K, B, N, maxiter)) return PMG_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
 
   MstepParams p;
-  p.K = K; p.B = B; p.N = N; p.Phi = Phi; p.yw = yw; p.tw = tw;
+  p.K = K; p.B = B; p.N = N; p.Phi = Phi; p.yw = yw; p.tw = tw; p.ldyw = ldyw; p.tws = tw_stride;
   p.prior_std = prior_std; p.lr = lr; p.b1 = b1; p.b2 = b2; p.eps = eps;
   p.maxiter = maxiter; p.tol = tol; p.min_iters = min_iters;
   p.W = W; p.mu = mu; p.nu = nu; p.count = count; p.loss_hist = loss_hist; p.err_hist = err_hist;

@@ -28,6 +28,9 @@ struct TransDev {
 struct ScanCommon {
   int64_t T, core_begin, core_end, chunk_len;
   int n_chain, halo, left_exact, right_exact;
+  int halo_next;            // warm-up length of the NEXT pass: where warm_out messages are taken
+  const float* sel_err;     // mode 2: chain s runs iff !(sel_err[s] <= sel_tol)
+  float sel_tol;
   float scale;
   TransDev tr;
   const float* ll;
@@ -200,6 +203,7 @@ __device__ __forceinline__ bool chain_range(const ScanCommon& c, int grp, ChainR
     r.s = idx;
   }
   if (r.s < 0 || r.s >= c.n_chain) return false;
+  if (c.mode == 2 && c.sel_err[r.s] <= c.sel_tol) return false;   // device-side selection (NaN selects)
   r.t_begin = c.core_begin + (int64_t)r.s * c.chunk_len;
   r.t_end = r.t_begin + c.chunk_len;
   if (r.t_end > c.core_end) r.t_end = c.core_end;
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
   float al0[Q], al1[Q];
   bool from_array = false;
   const float* src = nullptr;
-  if (c.mode == 1) {
+  if (c.mode != 0) {
     t0 = cr.t_begin;
     if (p.warm_in) { from_array = true; src = p.warm_in + (size_t)cr.s * p.warm_stride; }   // snapshot of the carry
     else if (t0 > 0) { from_array = true; src = p.alpha + (size_t)(t0 - 1) * 2 * K; }
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
         }
       }
     }
-    if (p.warm_out && t == cr.t_end - c.halo - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
+    if (p.warm_out && t == cr.t_end - c.halo_next - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
       float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
   // ---- where the recursion starts
   int64_t t_hi;
   const float* init = nullptr;
-  if (c.mode == 1) {
+  if (c.mode != 0) {
     if (cr.t_end < c.T) {
       t_hi = cr.t_end;
       init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
         }
       }
     }
-    if (p.warm_out && t == cr.t_begin + c.halo - 1 && (cr.s >= 1 || !c.left_exact)) {
+    if (p.warm_out && t == cr.t_begin + c.halo_next - 1 && (cr.s >= 1 || !c.left_exact)) {
       float* o = p.warm_out + ((int64_t)cr.s - 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -636,11 +640,13 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
 // ============================================================================
 // seam verification
 // ============================================================================
-__global__ void seam_check_kernel(int n, int len, const float* est, int64_t ld_est, const float* truth,
-                                  int64_t ld_truth, float floor_val, float* err) {
+// tol >= 0: seams with !(err <= tol) are counted into *counter (if given) and, with fix != 0, their estimate is
+// overwritten by the truth: the snapshot a conditional restart (scan mode 2) of that chain starts from.
+__global__ void seam_check_kernel(int n, int len, float* est, int64_t ld_est, const float* truth,
+                                  int64_t ld_truth, float floor_val, float* err, float tol, int fix, float* counter) {
   const int i = blockIdx.x;
   if (i >= n) return;
-  const float* a = est + (size_t)i * ld_est;
+  float* a = est + (size_t)i * ld_est;
   const float* b = truth + (size_t)i * ld_truth;
   __shared__ float sm[2][32];
   __shared__ float tot[2];
@@ -673,6 +679,13 @@ __global__ void seam_check_kernel(int n, int len, const float* est, int64_t ld_e
     float r = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sm[0][w]);
     err[i] = r;
+    tot[0] = r;
+    if (tol >= 0.f && !(r <= tol) && counter) atomicAdd(counter, 1.f);
+  }
+  if (tol >= 0.f && fix) {
+    __syncthreads();
+    if (!(tot[0] <= tol))
+      for (int j = threadIdx.x; j < len; j += blockDim.x) a[j] = b[j];
   }
 }
 
@@ -781,9 +794,13 @@ static int fill_common(ScanCommon& c, const pmg_scan_plan* plan, const pmg_trans
   if (tr->kind == 1 && (!tr->band_fwd || !tr->band_bwd)) return PMG_ERR_BAD_ARG;
   if (tr->kind != 0 && tr->kind != 1) return PMG_ERR_BAD_ARG;
   if (mode == 1 && (!chain_ids || n_ids <= 0)) return PMG_ERR_BAD_ARG;
+  if (mode == 2 && !plan->sel_err) return PMG_ERR_BAD_ARG;
+  if (mode < 0 || mode > 2 || plan->halo_next < 0) return PMG_ERR_BAD_ARG;
   if (ldll < tr->K) return PMG_ERR_BAD_ARG;
   c.T = plan->T; c.core_begin = plan->core_begin; c.core_end = plan->core_end;
   c.chunk_len = plan->chunk_len; c.n_chain = plan->n_chain; c.halo = plan->halo;
+  c.halo_next = plan->halo_next > 0 ? plan->halo_next : plan->halo;
+  c.sel_err = plan->sel_err; c.sel_tol = plan->sel_tol;
   c.left_exact = plan->left_exact; c.right_exact = plan->right_exact;
   c.scale = plan->likelihood_scale;
   c.tr.K = tr->K; c.tr.kind = tr->kind; c.tr.W = tr->W;
@@ -818,7 +835,7 @@ extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr,
   int rc = pmg::fill_common(p.c, plan, tr, ll, ldll, mode, chain_ids, n_ids);
   if (rc) return rc;
   if (!alpha) return PMG_ERR_BAD_ARG;
-  if (mode == 1 && !beta_end && !warm_in) return PMG_ERR_BAD_ARG;
+  if (mode != 0 && !beta_end && !warm_in) return PMG_ERR_BAD_ARG;
   if (gamma16 && (ldg < tr->K || (ldg & 7))) return PMG_ERR_BAD_ARG;
   p.alpha = alpha; p.beta_in = beta_in; p.warm_in = warm_in; p.warm_stride = warm_stride; p.warm_out = warm_out;
   p.gamma = gamma; p.gamma_lat = gamma_lat; p.dyn_marg = dyn_marg;
@@ -832,7 +849,19 @@ extern "C" int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, 
                               int64_t ld_truth, float floor_val, float* err, pmg_stream_t stream) {
   if (n <= 0) return PMG_OK;
   if (!est || !truth || !err || len <= 0) return PMG_ERR_BAD_ARG;
-  pmg::seam_check_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, len, est, ld_est, truth, ld_truth, floor_val, err);
+  pmg::seam_check_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, len, const_cast<float*>(est), ld_est, truth, ld_truth,
+                                                              floor_val, err, -1.f, 0, nullptr);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_seam_check_fix(int n, int len, float* est, int64_t ld_est, const float* truth, int64_t ld_truth,
+                                  float floor_val, float tol, int fix, float* err, float* counter,
+                                  pmg_stream_t stream) {
+  if (n <= 0) return PMG_OK;
+  if (!est || !truth || !err || len <= 0 || !(tol >= 0.f)) return PMG_ERR_BAD_ARG;
+  pmg::seam_check_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, len, est, ld_est, truth, ld_truth, floor_val, err,
+                                                              tol, fix, counter);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

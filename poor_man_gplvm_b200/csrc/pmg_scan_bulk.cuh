@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
     int idx = blockIdx.x * NW + grp;
     if (c.mode == 1) { if (idx >= c.n_ids) return; cr.s = c.chain_ids[idx]; } else cr.s = idx;
     if (cr.s < 0 || cr.s >= c.n_chain) return;
+    if (c.mode == 2 && c.sel_err[cr.s] <= c.sel_tol) return;
     cr.t_begin = c.core_begin + (int64_t)cr.s * c.chunk_len;
     cr.t_end = cr.t_begin + c.chunk_len;
     if (cr.t_end > c.core_end) cr.t_end = c.core_end;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
   int64_t t0;
   float v0[Q], v1[Q];
   const float* src = nullptr;
-  if (c.mode == 1) {
+  if (c.mode != 0) {
     t0 = cr.t_begin;
     if (p.warm_in) src = p.warm_in + (size_t)cr.s * p.warm_stride;     // snapshot of the carry
     else if (t0 > 0) src = p.alpha + (size_t)(t0 - 1) * 2 * K;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = v0[q] * inv_prev; o[K + x0 + q] = v1[q] * inv_prev; }
     }
-    if (p.warm_out && t == cr.t_end - c.halo - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
+    if (p.warm_out && t == cr.t_end - c.halo_next - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
       float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q)
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
     int idx = blockIdx.x * NW + grp;
     if (c.mode == 1) { if (idx >= c.n_ids) return; cr.s = c.chain_ids[idx]; } else cr.s = idx;
     if (cr.s < 0 || cr.s >= c.n_chain) return;
+    if (c.mode == 2 && c.sel_err[cr.s] <= c.sel_tol) return;
     cr.t_begin = c.core_begin + (int64_t)cr.s * c.chunk_len;
     cr.t_end = cr.t_begin + c.chunk_len;
     if (cr.t_end > c.core_end) cr.t_end = c.core_end;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
 
   int64_t t_hi;
   const float* init = nullptr;
-  if (c.mode == 1) {
+  if (c.mode != 0) {
     if (cr.t_end < c.T) {
       t_hi = cr.t_end;
       init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = b0[q] * inv; o[K + x0 + q] = b1[q] * inv; }
     }
-    if (p.warm_out && t == cr.t_begin + c.halo - 1 && (cr.s >= 1 || !c.left_exact)) {
+    if (p.warm_out && t == cr.t_begin + c.halo_next - 1 && (cr.s >= 1 || !c.left_exact)) {
       float* o = p.warm_out + ((int64_t)cr.s - 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q)

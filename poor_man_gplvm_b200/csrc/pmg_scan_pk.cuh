@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
     const int idx = blockIdx.x * NW + grp;
     if (c.mode == 1) { if (idx >= c.n_ids) return; cr.s = c.chain_ids[idx]; } else cr.s = idx;
     if (cr.s < 0 || cr.s >= c.n_chain) return;
+    if (c.mode == 2 && c.sel_err[cr.s] <= c.sel_tol) return;
     cr.t_begin = c.core_begin + (int64_t)cr.s * c.chunk_len;
     cr.t_end = cr.t_begin + c.chunk_len;
     if (cr.t_end > c.core_end) cr.t_end = c.core_end;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   // ---- initial carry
   int64_t t0;
   const float* src = nullptr;
-  if (c.mode == 1) {
+  if (c.mode != 0) {
     t0 = cr.t_begin;
     if (p.warm_in) src = p.warm_in + (size_t)cr.s * p.warm_stride;
     else if (t0 == 0 && p.carry_in) src = p.carry_in;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   const int n_steps = (int)(cr.t_end - t0);
   const int i_begin = (int)(cr.t_begin - t0);                    // first bin whose row is stored
   const int e_halo = p.halo_state ? i_begin - 1 : -1;            // warmed-up message in front of the chain
-  const int e_warm = (p.warm_out && (cr.s + 1 < c.n_chain || !c.right_exact)) ? (int)(cr.t_end - c.halo - 1 - t0) : -1;
+  const int e_warm = (p.warm_out && (cr.s + 1 < c.n_chain || !c.right_exact)) ? (int)(cr.t_end - c.halo_next - 1 - t0) : -1;
   const int e_end = p.fwd_end ? n_steps - 1 : -1;
   const int e_first = (p.first_out && cr.t_begin == c.core_begin) ? i_begin : -1;
   int evt = next_event(-1, e_halo, e_warm, e_end, e_first);
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
     const int idx = blockIdx.x * NW + grp;
     if (c.mode == 1) { if (idx >= c.n_ids) return; cr.s = c.chain_ids[idx]; } else cr.s = idx;
     if (cr.s < 0 || cr.s >= c.n_chain) return;
+    if (c.mode == 2 && c.sel_err[cr.s] <= c.sel_tol) return;
     cr.t_begin = c.core_begin + (int64_t)cr.s * c.chunk_len;
     cr.t_end = cr.t_begin + c.chunk_len;
     if (cr.t_end > c.core_end) cr.t_end = c.core_end;
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
 
   int64_t t_hi;
   const float* init = nullptr;
-  if (c.mode == 1) {
+  if (c.mode != 0) {
     if (cr.t_end < c.T) {
       t_hi = cr.t_end;
       init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
   const int i_core = (int)(t_hi - (cr.t_end - 1));               // first step of the chain's own bins
   const int e_halo = (p.beta_halo && i_alpha >= 0) ? i_alpha : -1;          // t == t_end
   const int e_end = p.beta_end ? n_steps - 1 : -1;                          // t == t_begin
-  const int e_warm = (p.warm_out && (cr.s >= 1 || !c.left_exact)) ? (int)(t_hi - (cr.t_begin + c.halo - 1)) : -1;
+  const int e_warm = (p.warm_out && (cr.s >= 1 || !c.left_exact)) ? (int)(t_hi - (cr.t_begin + c.halo_next - 1)) : -1;
   int evt = next_event(-1, e_halo, e_end, e_warm, -1);
 
   const uint32_t row_bytes = (uint32_t)K * 4;
@@ -704,7 +706,7 @@ extern "C" int pmg_forward_compact(const pmg_scan_plan* plan, const pmg_transiti
   if (!ax || ldax < tr->K + 4 || (ldax & 3) || (ldll & 3)) return PMG_ERR_BAD_ARG;
   if (!pmg_scan_compact_supported(tr, plan->likelihood_scale)) return PMG_ERR_UNSUPPORTED_SHAPE;
   if (((uintptr_t)ll | (uintptr_t)ax) & 15) return PMG_ERR_ALIGNMENT;
-  if (mode == 1 && !warm_in) return PMG_ERR_BAD_ARG;      // relays restart from a snapshot of the carry
+  if (mode != 0 && !warm_in) return PMG_ERR_BAD_ARG;      // relays restart from a snapshot of the carry
   p.carry_in = carry_in; p.warm_in = warm_in; p.warm_stride = warm_stride; p.warm_out = warm_out;
   p.ax = ax; p.ldax = ldax; p.halo_state = halo_state; p.fwd_end = fwd_end; p.first_out = first_out;
   const int n_groups = mode == 1 ? n_ids : plan->n_chain;
@@ -723,7 +725,7 @@ extern "C" int pmg_backward_compact(const pmg_scan_plan* plan, const pmg_transit
   if (!gamma16 || ldg < tr->K || (ldg & 7)) return PMG_ERR_BAD_ARG;
   if (!pmg_scan_compact_supported(tr, plan->likelihood_scale)) return PMG_ERR_UNSUPPORTED_SHAPE;
   if (((uintptr_t)ll | (uintptr_t)ax | (uintptr_t)gamma16) & 15) return PMG_ERR_ALIGNMENT;
-  if (mode == 1 && !beta_end && !warm_in) return PMG_ERR_BAD_ARG;
+  if (mode != 0 && !beta_end && !warm_in) return PMG_ERR_BAD_ARG;
   p.ax = ax; p.ldax = ldax; p.beta_in = beta_in; p.warm_in = warm_in; p.warm_stride = warm_stride;
   p.warm_out = warm_out; p.gamma16 = (__half*)gamma16; p.ldg = ldg;
   p.beta_halo = beta_halo; p.beta_end = beta_end;

@@ -6,11 +6,29 @@ sequentially; here the time axis is cut into ``n_chain`` chunks ("chains") that 
 concurrently, on one GPU or on a contiguous time block per rank.  A chain warms
 up over ``halo`` bins starting from the previous pass's message at that bin (or
 the stationary distribution of the prior chain on the first pass);
-``pmg_seam_check`` then compares the warmed-up message with the neighbouring
-chain's true one, and failing chains are restarted in parallel sweeps from a
-snapshot of the neighbour's boundary message until every seam agrees to
-``seam_tol`` (worst case this degenerates to the reference's sequential walk,
-so the result never depends on the chunking beyond ``seam_tol``).
+``pmg_seam_check_fix`` then compares the warmed-up message with the neighbouring
+chain's true one.
+
+Seams that miss ``seam_tol`` are repaired in two tiers:
+
+* on the device, with no host round trip: the check overwrites the failed estimate
+  by the neighbour's true boundary message and a *conditional* relaunch of the pass
+  (scan mode 2) re-runs exactly those chains from that snapshot; the other chains'
+  warps return at once.  The forward repair runs before the backward pass, so the
+  smoother already sees the repaired filtered posterior.  This is the common case
+  (a few slow-mixing seams per thousand on a fitted model, most seams of a flat one);
+* on the host (Jacobi sweeps, as in round 1) if a seam still fails the re-check:
+  failing chains restart all at once from their neighbours' current boundary
+  messages until every seam passes; worst case this degenerates to the reference's
+  sequential walk, so the result never depends on the chunking beyond ``seam_tol``.
+
+One host synchronisation per E-step: a 5-float record (log marginal, seams repaired on
+the device and seams still failing, per pass) plus the seam errors.  On time-sharded
+runs that record travels in the caller's packed statistics all-reduce
+(``before_sync``), so an EM iteration has ONE collective besides the two boundary
+exchanges.  The warm-up length adapts between ``halo_min`` and the initial ``halo``
+(EM mode): it halves while no seam needs a repair and grows back when repairs would
+cost more than the longer warm-up.
 """
 from __future__ import annotations
 
@@ -22,42 +40,52 @@ from . import ops
 from .shard import TimeShard
 
 DEFAULT_HALO = int(os.environ.get("PMG_HALO", "256"))
+DEFAULT_HALO_MIN = int(os.environ.get("PMG_HALO_MIN", "32"))
 DEFAULT_SEAM_TOL = float(os.environ.get("PMG_SEAM_TOL", "1e-5"))
-MIN_CHUNK_OVER_HALO = int(os.environ.get("PMG_MIN_CHUNK_OVER_HALO", "2"))
+MIN_CHUNK = int(os.environ.get("PMG_MIN_CHUNK", "64"))
 # chains per SM of an EM-mode plan on the compact kernels (12 warps per CTA, 3 per scheduler); 8 elsewhere
-EM_CHAINS_PER_SM = int(os.environ.get("PMG_EM_CHAINS_PER_SM", "12"))
+EM_CHAINS_PER_SM = 12
+
+# record shared with the caller's collective: log marginal, then (repaired on device, still failing) per pass
+TAIL = 5
+T_LML, T_FIX_F, T_FAIL_F, T_FIX_B, T_FAIL_B = range(TAIL)
 
 
-def plan_chunks(n_core, halo, sm_count, chains_per_sm=8):
-    """chunk length: at least MIN_CHUNK_OVER_HALO x halo (bounded warm-up overhead),
-    at most what fills `sm_count * chains_per_sm` chains."""
+def plan_chunks(n_core, halo, sm_count, chains_per_sm=8, min_chunk=None):
+    """chunk length: what fills `sm_count * chains_per_sm` chains, but at least `min_chunk` bins (bounded
+    warm-up overhead: the warm-up adapts down to DEFAULT_HALO_MIN in EM mode; one-shot passes keep
+    chunks of at least 2 x halo)."""
     if halo <= 0:
         return n_core
+    if min_chunk is None:
+        min_chunk = 2 * halo
     target = max(1, sm_count * chains_per_sm)
-    chunk = max(MIN_CHUNK_OVER_HALO * halo, (n_core + target - 1) // target)
+    chunk = max(int(min_chunk), (n_core + target - 1) // target)
     return min(chunk, n_core)
 
 
 class EStepResult:
     """Tensors cover this rank's core bins only (views into the E-step buffers)."""
     __slots__ = ("ll", "alpha", "lmr", "gamma", "gamma_lat", "dyn_marg", "r", "tw", "log_marginal",
-                 "n_relay_fwd", "n_relay_bwd", "seam_err_fwd", "seam_err_bwd", "plan", "alpha_ext", "r_ext", "core",
-                 "repaired")
+                 "n_relay_fwd", "n_relay_bwd", "n_fix_fwd", "n_fix_bwd", "seam_err_fwd", "seam_err_bwd", "plan",
+                 "alpha_ext", "r_ext", "core", "repaired", "halo")
 
 
 class EStep:
     """Buffers and launch plan for repeated E-steps over the same spike matrix (this rank's block)."""
 
     def __init__(self, y, op, ma_neuron=None, ma_latent=None, likelihood_scale=1.0, halo=None, seam_tol=None,
-                 chunk_len=None, emission_impl=0, shard=None, em_mode=False):
-        """em_mode: the plan is sized for the compact EM kernels (more, shorter chains) when they apply."""
+                 chunk_len=None, emission_impl=0, shard=None, em_mode=False, tail=None, adaptive=None):
+        """em_mode: the plan is sized for the compact EM kernels (more, shorter chains) when they apply and the
+        warm-up length adapts from pass to pass.  tail: optional 5-float device view the E-step writes its record
+        into (the caller all-reduces it together with its own data inside ``before_sync``)."""
         self.op = op
         self.K = op.K
         self.dev = y.device
         self.ma_neuron = ma_neuron
         self.ma_latent = ma_latent
         self.scale = float(likelihood_scale)
-        self.halo = DEFAULT_HALO if halo is None else int(halo)
+        self.halo = DEFAULT_HALO if halo is None else int(halo)       # widest warm-up = rows fetched from neighbours
         self.seam_tol = DEFAULT_SEAM_TOL if seam_tol is None else float(seam_tol)
         self.emission_impl = emission_impl
         self.shard = shard if shard is not None else TimeShard(None, single=True)
@@ -70,12 +98,22 @@ class EStep:
         self.sm_count = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.compact_ok = (os.environ.get("PMG_SCAN_COMPACT", "1") != "0"
                            and ops.scan_compact_supported(op, self.scale))
+        if adaptive is None:
+            adaptive = em_mode and os.environ.get("PMG_HALO_ADAPT", "1") != "0"
+        self.adaptive = bool(adaptive) and self.halo > 0
+        # tier 1 of the seam repair (conditional relaunch on the device); off = every repair is a host sweep
+        self.device_repair = os.environ.get("PMG_DEVICE_REPAIR", "1") != "0"
+        self.halo_min = min(self.halo, DEFAULT_HALO_MIN)
         if chunk_len is None:
             wide = em_mode and self.compact_ok and self.K > 31 * 8       # the 12-chain variants exist for K > 248
-            chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count, EM_CHAINS_PER_SM if wide else 8)
+            chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count, EM_CHAINS_PER_SM if wide else 8,
+                                    min_chunk=(min(MIN_CHUNK, 2 * self.halo) if self.adaptive else None))
         self.chunk_len = int(min(max(1, chunk_len), self.T_core))
+        # warm-up of this pass and of the next one (the pass writes the next pass's warm-start messages)
+        self.halos = [self.halo, self.halo]
+        self._calm, self._hold = 0, 0
         self.plan = ops.make_plan(self.T, self.core.start, self.core.stop, self.chunk_len, self.halo,
-                                  self.shard.is_first, self.shard.is_last, self.scale)
+                                  self.shard.is_first, self.shard.is_last, self.scale, halo_next=self.halo)
         S = self.plan.n_chain
         self.S = S
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -94,13 +132,14 @@ class EStep:
         self._alpha = None                 # [T,2,K] filtered posterior of the general path (allocated on first use)
         self._ax = None                    # [T,K+4] compact filtered posterior of the EM fast path
         self.lmr = torch.zeros(self.T, **f32)
-        self.fwd_end = torch.zeros((S, 2, self.K), **f32)       # true message at the last bin of each chain
+        # true message at the last bin of each chain, one slot ahead: slot 0 holds the left neighbour rank's last
+        # message, chain c writes slot c+1, so seam c (in front of chain c) always finds its truth in slot c
+        self.fwd_end_ext = torch.zeros((S + 1, 2, self.K), **f32)
+        self.fwd_end = self.fwd_end_ext[1:]
         self.first_out = torch.zeros((2, self.K), **f32)        # true message at the first core bin
         self.halo_state = torch.zeros((S, 2, self.K), **f32)
         self.beta_halo = torch.zeros((S, 2, self.K), **f32)
         self.beta_end = torch.zeros((S + 1, 2, self.K), **f32)     # [S] = the right neighbour's first chain
-        self.truth = torch.zeros((S, 2, self.K), **f32)
-        self.truth_left = None
         self.tw_partial = torch.zeros((S, self.K), **f32)
         # warm-up starts: ping-pong buffers holding, for every chain, the message of the previous pass
         # at the bin where its warm-up starts (forward and backward); before the first pass the forward
@@ -122,12 +161,15 @@ class EStep:
         self.warm_valid = False
         self.err = torch.zeros(2 * S, **f32)
         self.err_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
-        self._gmax_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        # rows of alpha holding the true message in front of chain c (c >= 1): bin t_begin(c) - 1
-        self.rows_f = self.core.start + torch.arange(1, S, device=self.dev) * self.chunk_len - 1
+        self.tail = tail if tail is not None else torch.zeros(TAIL, **f32)
+        if self.tail.numel() != TAIL or self.tail.dtype != torch.float32 or not self.tail.is_contiguous():
+            raise ValueError("tail must be a contiguous float32 view of %d entries" % TAIL)
+        self.tail_host = torch.zeros(TAIL, dtype=torch.float32).pin_memory()
         # which seams exist: forward seam c sits in front of chain c; backward seam c behind chain c
         self.f_lo = 0 if not self.shard.is_first else 1
         self.b_hi = S if not self.shard.is_last else S - 1
+        # host repair sweeps: same bound on every rank (block lengths, hence S, may differ between ranks)
+        self.max_sweeps = self.shard.max_int(S, self.dev) * self.shard.world + 2
 
     @property
     def alpha(self):
@@ -158,10 +200,10 @@ class EStep:
         else:
             first = self.alpha[self.core.start].reshape(-1)
             last = self.alpha[self.core.stop - 1].reshape(-1)
-        # message at the bin in front of the right neighbour's first warm-up bin.  The kernels' slot S holds it
-        # only when that bin lies in the last chain's own range; with a ragged (short) last chunk it lies in an
-        # earlier chain, so it is read back from the stored filtered posterior instead.
-        t_star = self.core.stop - self.halo - 1
+        # message at the bin in front of the right neighbour's first warm-up bin (of the NEXT pass).  The kernels'
+        # slot S holds it only when that bin lies in the last chain's own range; with a ragged (short) last chunk
+        # it lies in an earlier chain, so it is read back from the stored filtered posterior instead.
+        t_star = self.core.stop - self.halos[1] - 1
         if nxt is None:
             warm = torch.zeros_like(last)
         elif t_star < self.core.start:
@@ -175,7 +217,7 @@ class EStep:
         from_left, from_right = self.shard.boundary(torch.cat([first, torch.zeros_like(first)]),
                                                     torch.cat([last, warm]))
         if from_left is not None:
-            self.truth_left = from_left[:K2].view(2, self.K)
+            self.fwd_end_ext[0].copy_(from_left[:K2].view(2, self.K))
             w = from_left[K2:]
             if nxt is not None:
                 self.fwarm[nxt][0].copy_(w.view(2, self.K))
@@ -205,59 +247,98 @@ class EStep:
             if nxt is not None:
                 self.bwarm[nxt][self.S].copy_(from_right[K2:].view(2, self.K))
 
-    def _check_fwd(self, compact=False):
+    def _check_fwd(self, compact, lo, fix, counter):
+        """Forward seams lo..S-1 (seam c sits in front of chain c): warmed-up estimate vs the true message.
+        fix: failed estimates are replaced by the truth (the snapshot a mode-2 restart starts from)."""
         S, K2 = self.S, 2 * self.K
-        if S > 1:
-            self.truth[1:] = self.fwd_end[:-1] if compact else self.alpha[self.rows_f]
+        if lo >= S:
+            return
+        est = self.halo_state
+        if compact:
+            ops.seam_check_fix(S - lo, K2, est[lo].data_ptr(), K2, self.fwd_end_ext[lo].data_ptr(), K2,
+                               self.err[lo:S], self.seam_tol, fix, counter)
+            return
+        if lo == 0:         # the left neighbour rank's message
+            ops.seam_check_fix(1, K2, est[0].data_ptr(), K2, self.fwd_end_ext[0].data_ptr(), K2, self.err[0:1],
+                               self.seam_tol, fix, counter)
+            lo = 1
+        if lo < S:          # true message in front of chain c >= 1: row t_begin(c) - 1 of the filtered posterior
+            row = self.alpha[self.core.start + lo * self.chunk_len - 1]
+            ops.seam_check_fix(S - lo, K2, est[lo].data_ptr(), K2, row.data_ptr(), self.chunk_len * K2,
+                               self.err[lo:S], self.seam_tol, fix, counter)
+
+    def _check_bwd(self, hi, fix, counter):
+        """Backward seams 0..hi-1 (seam c sits behind chain c; its truth is the next chain's first message)."""
+        S, K2 = self.S, 2 * self.K
+        if hi > 0:
+            ops.seam_check_fix(hi, K2, self.beta_halo.data_ptr(), K2, self.beta_end[1].data_ptr(), K2,
+                               self.err[S:S + hi], self.seam_tol, fix, counter)
+
+    def _truth_fwd(self, ids, compact):
+        """true forward messages in front of the chains `ids` (host repair sweeps)"""
+        if compact:
+            return self.fwd_end_ext[ids]
+        rows = self.core.start + ids * self.chunk_len - 1
+        out = self.alpha[rows.clamp_min(0)]
         if self.f_lo == 0:
-            self.truth[0] = self.truth_left
-        n = S - self.f_lo
-        if n > 0:
-            ops.seam_check(n, K2, self.halo_state[self.f_lo:].data_ptr(), K2, self.truth[self.f_lo:].data_ptr(), K2,
-                           self.err[self.f_lo:S])
+            out = torch.where((ids == 0).view(-1, 1, 1), self.fwd_end_ext[0].unsqueeze(0), out)
+        return out
 
-    def _check_bwd(self):
-        S, K2 = self.S, 2 * self.K
-        n = self.b_hi
-        if n > 0:
-            ops.seam_check(n, K2, self.beta_halo.data_ptr(), K2, self.beta_end[1:].data_ptr(), K2,
-                           self.err[S:S + n])
+    def _lml_to_tail(self, lmr):
+        self.tail[T_LML:T_LML + 1].copy_(lmr[self.core].sum(dim=0, keepdim=True, dtype=torch.float64))
 
-    def _read_err(self):
+    def _verdict(self, before_sync=None):
+        """Brings the record (and the seam errors) to the host: the ONE synchronisation of an E-step.  On
+        time-sharded runs the record is summed over ranks -- inside the caller's collective when ``before_sync``
+        performs one (it must all-reduce ``self.tail``), else here."""
+        if before_sync is not None:
+            before_sync()
+        elif self.shard.active:
+            self.shard.allreduce_flat_sum_(self.tail)
+        self.tail_host.copy_(self.tail, non_blocking=True)
         self.err_host.copy_(self.err, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.err_host
+        t = self.tail_host
+        return self.err_host, bool(not (t[T_FAIL_F] == 0)), bool(not (t[T_FAIL_B] == 0))
 
-    def _read_err_global(self):
-        """Seam errors of this rank plus, for time-sharded runs, whether ANY rank has a failing forward /
-        backward seam -- one collective and one synchronisation for the common case of no repair at all."""
-        if not self.shard.active:
-            err = self._read_err()
-            ef, eb = err[self.f_lo:self.S], err[self.S:self.S + self.b_hi]
-            return err, bool(ef.numel() and float(ef.max()) > self.seam_tol), \
-                bool(eb.numel() and float(eb.max()) > self.seam_tol)
-        S = self.S
-        zero = self.err.new_zeros(())
-        m = torch.stack([self.err[self.f_lo:S].max() if S > self.f_lo else zero,
-                         self.err[S:S + self.b_hi].max() if self.b_hi > 0 else zero])
-        m = torch.nan_to_num(m, nan=float("inf"))
-        self.shard.allreduce_max_(m)
-        self._gmax_host.copy_(m, non_blocking=True)
-        err = self._read_err()
-        return err, bool(self._gmax_host[0] > self.seam_tol), bool(self._gmax_host[1] > self.seam_tol)
+    def _adapt(self, n_fix):
+        """Warm-up of the pass after next from this pass's record (identical on every rank: the record is global).
+        A device repair costs about one chunk of scan time at low occupancy; a longer warm-up costs every chain:
+        repairs are tolerated while the chunks are short compared with the warm-up they would save."""
+        cur, nxt = self.halos
+        new = nxt
+        if self.adaptive:
+            tolerated = self.chunk_len <= 2 * nxt
+            if n_fix > 0 and not tolerated:
+                self._calm = 0
+                if nxt < self.halo:
+                    new = min(self.halo, 2 * nxt)
+                    self._hold = 8
+            elif n_fix == 0:
+                self._calm += 1
+                if self._calm >= 2 and self._hold == 0 and nxt > self.halo_min:
+                    new = max(self.halo_min, nxt // 2)
+                    self._calm = 0
+            else:
+                self._calm = 0
+            if self._hold:
+                self._hold -= 1
+        self.halos = [nxt, new]
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
             before_sync=None):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
-        the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes and
-        the seam checks are enqueued, before the launching thread waits for the verdict (work enqueued there
-        keeps the GPU busy during the synchronisation; ``res.repaired`` tells whether chains were re-run after
-        it, i.e. whether what it read from this E-step's outputs was final)."""
+        the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes, the
+        device repairs and the seam checks are enqueued, before the launching thread waits for the verdict (work
+        enqueued there keeps the GPU busy during the synchronisation; on time-sharded runs it must all-reduce
+        ``self.tail`` with its own data; ``res.repaired`` tells whether chains were re-run by the HOST after it,
+        i.e. whether what it read from this E-step's outputs was final)."""
         S, K = self.S, self.K
         f32 = dict(dtype=torch.float32, device=self.dev)
         # EM fast path: only the fp16 posterior pieces and sum_t gamma are wanted -> compact kernels
         compact = (self.compact_ok and gamma16 is not None
                    and not (want_gamma or want_gamma_lat or want_dyn or want_r))
+        self.plan.halo, self.plan.halo_next = int(self.halos[0]), int(self.halos[1])
         self.emission(tuning)
         ops.phase("emission")
         gamma = torch.empty((self.T, 2, K), **f32) if want_gamma else None
@@ -269,87 +350,109 @@ class EStep:
         f_in = self.fwarm[cur] if self.warm_valid else getattr(self.op, "stationary", None)
         b_in = self.bwarm[cur][1:] if self.warm_valid else None
         b_out = self.bwarm[nxt][1:]
+        err_f, err_b = self.err[0:S], self.err[S:2 * S]
+        tol = self.seam_tol
 
         def fwd(mode=0, ids=None):
+            sel = dict(sel_err=err_f, sel_tol=tol) if mode == 2 else {}
             if compact:
                 ops.forward_compact(self.plan, self.op, self.ll, self.ax,
                                     halo_state=(self.halo_state if mode == 0 else None), fwd_end=self.fwd_end,
                                     first_out=self.first_out, mode=mode, chain_ids=ids,
-                                    warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt])
+                                    warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt], **sel)
                 return
             ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr,
                         halo_state=(self.halo_state if mode == 0 else None), mode=mode, chain_ids=ids,
-                        warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt])
+                        warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt], **sel)
 
         def bwd(mode=0, ids=None):
+            sel = dict(sel_err=err_b, sel_tol=tol) if mode == 2 else {}
             if compact:
-                ops.backward_compact(self.plan, self.op, self.ll, self.ax, gamma16, beta_halo=self.beta_halo, beta_end=self.beta_end, mode=mode, chain_ids=ids,
-                                     warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out)
+                ops.backward_compact(self.plan, self.op, self.ll, self.ax, gamma16, beta_halo=self.beta_halo,
+                                     beta_end=self.beta_end, mode=mode, chain_ids=ids,
+                                     warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out, **sel)
                 return
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
                          mode=mode, chain_ids=ids, gamma16=gamma16,
-                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out)
+                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out, **sel)
 
+        seams = S > 1 or self.shard.active
+        lmr = self.ax[:, K + 1] if compact else self.lmr
+        self.tail.zero_()
+        # ---- forward: all chains; seams between this rank's own chains are verified and repaired on the device
+        # (conditional relaunch) before anything consumes the filtered posterior; the boundary seam to the left
+        # neighbour rank is verified after the exchange (its repair, rare, is the host's)
         fwd()
+        if S > 1 and self.device_repair:
+            self._check_fwd(compact, 1, True, self.tail[T_FIX_F:T_FIX_F + 1])
+            fwd(mode=2)
         self._exchange_fwd(compact, nxt)
-        self._check_fwd(compact)
+        if seams:
+            self._check_fwd(compact, self.f_lo, False, self.tail[T_FAIL_F:T_FAIL_F + 1])
+        self._lml_to_tail(lmr)
         ops.phase("forward")
+        # ---- backward, same structure
         bwd()
+        if S > 1 and self.device_repair:
+            self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1])
+            bwd(mode=2)
         self._exchange_bwd(nxt)
-        self._check_bwd()
+        if seams:
+            self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
         ops.phase("backward")
 
         n_relay_f = n_relay_b = 0
-        ef = eb = torch.zeros(0)
-        any_f = any_b = False
-        if before_sync is not None:
-            before_sync()
-        if S > 1 or self.shard.active:
-            err, any_f, any_b = self._read_err_global()
-            ef = err[self.f_lo:S].clone()         # ef[i]: seam in front of chain f_lo + i
-            eb = err[S:S + self.b_hi].clone()     # eb[c]: seam behind chain c
-            # Seam repair = parallel (Jacobi) sweeps: every chain whose incoming message was off restarts,
-            # all at once (on all ranks), from a snapshot of its neighbour's current boundary message; the
-            # seams are then re-verified against the messages those restarts produced.  Each sweep extends
-            # the effective warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length.
-            # One sweep = forward restarts, then the backward pass of (a) the chains whose filtered posterior
-            # just changed -- from their own, already verified, incoming beta -- and (b) the chains whose
-            # incoming beta was off -- from the neighbour's; other chains' backward results do not depend on
-            # the re-run chains (beta does not involve alpha; normalisers are scale only).  One verdict
-            # (synchronisation + collective) per sweep.
-            repaired = bool(any_f or any_b)
-            for _ in range(S * self.shard.world + 2):
-                if not (any_f or any_b):
-                    break
-                bad_f = torch.nonzero(ef > self.seam_tol).flatten() + self.f_lo
-                bad_b = torch.nonzero(eb > self.seam_tol).flatten()
-                n_relay_f += int(bad_f.numel())
-                n_relay_b += int(bad_b.numel())
-                if bad_f.numel():
-                    ids = bad_f.to(device=self.dev, dtype=torch.int32)
-                    self.halo_state[ids.long()] = self.truth[ids.long()]      # carry snapshot = new "estimate"
-                    fwd(mode=1, ids=ids)
-                self._exchange_fwd(compact, nxt)
-                if bad_b.numel():
-                    idb = bad_b.to(device=self.dev)
-                    self.beta_halo[idb] = self.beta_end[idb + 1]
-                both = torch.unique(torch.cat([bad_f, bad_b]))
-                if both.numel():
-                    bwd(mode=1, ids=both.to(device=self.dev, dtype=torch.int32))
-                self._exchange_bwd(nxt)
-                self._check_fwd(compact)
-                self._check_bwd()
-                err, any_f, any_b = self._read_err_global()
-                ef = err[self.f_lo:S].clone()
-                eb = err[S:S + self.b_hi].clone()
-            any_f = any_b = repaired
+        err, any_f, any_b = self._verdict(before_sync)
+        n_fix_f, n_fix_b = int(self.tail_host[T_FIX_F]), int(self.tail_host[T_FIX_B])
+        repaired = bool(any_f or any_b)
+        # Host repair = parallel (Jacobi) sweeps: every chain whose incoming message is still off restarts,
+        # all at once (on all ranks), from a snapshot of its neighbour's current boundary message; the
+        # seams are then re-verified against the messages those restarts produced.  Each sweep extends
+        # the effective warm-up by one chunk, so the number of sweeps is ~ mixing length / chunk length.
+        # One sweep = forward restarts, then the backward pass of (a) the chains whose filtered posterior
+        # just changed -- from their own, already verified, incoming beta -- and (b) the chains whose
+        # incoming beta was off -- from the neighbour's; other chains' backward results do not depend on
+        # the re-run chains (beta does not involve alpha; normalisers are scale only).  One verdict
+        # (synchronisation + collective) per sweep.
+        for _ in range(self.max_sweeps):
+            if not (any_f or any_b):
+                break
+            ef, eb = err[self.f_lo:S], err[S:S + self.b_hi]
+            bad_f = torch.nonzero(~(ef <= tol)).flatten() + self.f_lo
+            bad_b = torch.nonzero(~(eb <= tol)).flatten()
+            n_relay_f += int(bad_f.numel())
+            n_relay_b += int(bad_b.numel())
+            if bad_f.numel():
+                idl = bad_f.to(device=self.dev)
+                self.halo_state[idl] = self._truth_fwd(idl, compact)          # carry snapshot = new "estimate"
+                fwd(mode=1, ids=idl.to(torch.int32))
+            self._exchange_fwd(compact, nxt)
+            if bad_b.numel():
+                idb = bad_b.to(device=self.dev)
+                self.beta_halo[idb] = self.beta_end[idb + 1]
+            both = torch.unique(torch.cat([bad_f, bad_b]))
+            if both.numel():
+                bwd(mode=1, ids=both.to(device=self.dev, dtype=torch.int32))
+            self._exchange_bwd(nxt)
+            self.tail.zero_()
+            self._check_fwd(compact, self.f_lo, False, self.tail[T_FAIL_F:T_FAIL_F + 1])
+            self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
+            self._lml_to_tail(lmr)
+            err, any_f, any_b = self._verdict()
+        if any_f or any_b:
+            raise RuntimeError("E-step: seams still above seam_tol=%g after %d repair sweeps (worst forward %.3g, "
+                               "backward %.3g)" % (tol, self.max_sweeps, float(err[self.f_lo:S].max()) if S > self.f_lo
+                                                   else 0.0, float(err[S:S + self.b_hi].max()) if self.b_hi else 0.0))
+        if seams:
             self.warm_cur, self.warm_valid = nxt, True
+        halo_used = self.halos[0]
+        self._adapt(n_fix_f + n_fix_b + n_relay_f + n_relay_b)
 
         c = self.core
+        ef, eb = err[self.f_lo:S], err[S:S + self.b_hi]
         res = EStepResult()
         res.core = c
-        lmr = self.ax[:, K + 1] if compact else self.lmr
         res.ll, res.lmr = self.ll[c], lmr[c]
         res.alpha = None if compact else self.alpha[c]
         res.alpha_ext, res.r_ext = (None if compact else self.alpha), r
@@ -360,10 +463,13 @@ class EStep:
         # local sums; the caller all-reduces them together with the spike-weighted statistics
         # (the compact path leaves sum_t gamma to the statistics GEMM: ones column of the fp16 counts)
         res.tw = None if compact else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
-        res.log_marginal = lmr[c].sum(dtype=torch.float64)
+        # global (summed over ranks) log marginal: a host scalar, it came with the verdict
+        res.log_marginal = self.tail_host[T_LML].clone()
         res.n_relay_fwd, res.n_relay_bwd = n_relay_f, n_relay_b
-        res.repaired = bool(any_f or any_b)                   # same verdict on every rank
+        res.n_fix_fwd, res.n_fix_bwd = n_fix_f, n_fix_b               # repaired on the device (all ranks)
+        res.repaired = repaired                                       # host sweeps ran; same verdict on every rank
         res.seam_err_fwd = float(ef.max()) if ef.numel() else 0.0
         res.seam_err_bwd = float(eb.max()) if eb.numel() else 0.0
         res.plan = self.plan
+        res.halo = halo_used
         return res

@@ -342,7 +342,7 @@ class MoveOperator:
         return s
 
 
-def make_plan(T, core_begin, core_end, chunk_len, halo, left_exact, right_exact, likelihood_scale):
+def make_plan(T, core_begin, core_end, chunk_len, halo, left_exact, right_exact, likelihood_scale, halo_next=0):
     p = PmgScanPlan()
     p.T, p.core_begin, p.core_end = int(T), int(core_begin), int(core_end)
     p.chunk_len = int(chunk_len)
@@ -350,7 +350,19 @@ def make_plan(T, core_begin, core_end, chunk_len, halo, left_exact, right_exact,
     p.halo = int(halo)
     p.left_exact, p.right_exact = int(bool(left_exact)), int(bool(right_exact))
     p.likelihood_scale = float(likelihood_scale)
+    p.halo_next = int(halo_next)
+    p.sel_tol, p.sel_err = 0.0, None
     return p
+
+
+def _select(plan, mode, sel_err, sel_tol):
+    """mode 2: the chains to re-run are selected on the device, chain s iff !(sel_err[s] <= sel_tol)."""
+    if mode == 2:
+        if sel_err is None or sel_err.numel() < plan.n_chain:
+            raise ValueError("mode 2 needs one seam error per chain")
+        plan.sel_err, plan.sel_tol = sel_err.data_ptr(), float(sel_tol)
+    else:
+        plan.sel_err, plan.sel_tol = None, 0.0
 
 
 def _warm(warm_in):
@@ -361,8 +373,9 @@ def _warm(warm_in):
 
 
 def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None, warm_in=None,
-            warm_out=None):
+            warm_out=None, sel_err=None, sel_tol=0.0):
     lib = _lib.load()
+    _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
@@ -374,8 +387,9 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
              beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
-             warm_out=None):
+             warm_out=None, sel_err=None, sel_tol=0.0):
     lib = _lib.load()
+    _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
@@ -394,9 +408,10 @@ def scan_compact_supported(op, likelihood_scale):
 
 
 def forward_compact(plan, op, ll, ax, halo_state=None, fwd_end=None, first_out=None, carry_in=None, mode=0,
-                    chain_ids=None, warm_in=None, warm_out=None):
+                    chain_ids=None, warm_in=None, warm_out=None, sel_err=None, sel_tol=0.0):
     """Forward pass writing the compact filtered posterior ax [T, K+4] (alpha[0,:], a1s, lmr per bin)."""
     lib = _lib.load()
+    _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
@@ -407,9 +422,10 @@ def forward_compact(plan, op, ll, ax, halo_state=None, fwd_end=None, first_out=N
 
 
 def backward_compact(plan, op, ll, ax, gamma16, beta_halo=None, beta_end=None, beta_in=None,
-                     mode=0, chain_ids=None, warm_in=None, warm_out=None):
+                     mode=0, chain_ids=None, warm_in=None, warm_out=None, sel_err=None, sel_tol=0.0):
     """Backward pass of an EM iteration: fp16 pieces of the latent posterior (and the seam messages)."""
     lib = _lib.load()
+    _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
@@ -427,6 +443,17 @@ def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1
     lib = _lib.load()
     check(lib.pmg_seam_check(int(n), int(length), C.c_void_p(est_ptr), int(ld_est), C.c_void_p(truth_ptr),
                              int(ld_truth), float(floor_val), _p(err), _stream()), "pmg_seam_check")
+    _count(1)
+
+
+def seam_check_fix(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, tol, fix=False, counter=None,
+                   floor_val=1e-12):
+    """seam_check that also counts the seams with !(err <= tol) into `counter` (one device float) and, with fix=True,
+    overwrites their estimate by the truth: the snapshot a mode-2 restart of that chain starts from."""
+    lib = _lib.load()
+    check(lib.pmg_seam_check_fix(int(n), int(length), C.c_void_p(est_ptr), int(ld_est), C.c_void_p(truth_ptr),
+                                 int(ld_truth), float(floor_val), float(tol), int(bool(fix)), _p(err), _p(counter),
+                                 _stream()), "pmg_seam_check_fix")
     _count(1)
 
 
@@ -457,7 +484,7 @@ def atb(A, B, out=None, impl=0):
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)
     nbytes = lib.pmg_atb_workspace_bytes(T, M, N, int(impl))
     ws = _workspace(nbytes, A.device)
-    check(lib.pmg_atb(T, M, N, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), N, _p(ws), ws.numel(), int(impl),
+    check(lib.pmg_atb(T, M, N, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), _p(ws), ws.numel(), int(impl),
                       _stream()), "pmg_atb")
     _count(2)
     return out
@@ -561,10 +588,14 @@ def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, t
     Returns device tensors (loss_hist[maxiter], err_hist[maxiter], n_iter[1] int32, final[2], tuning[K,N]);
     out: optional tuple of preallocated tensors of those shapes to write into."""
     lib = _lib.load()
-    _f32(Phi, "Phi", 2); _f32(yw, "yw", 2); _f32(tw, "tw", 1); _f32(W, "W", 2)
+    _f32(Phi, "Phi", 2); _f32(W, "W", 2)
     K, B = Phi.shape
     N = W.shape[1]
-    if W.shape[0] != B or yw.shape != (K, N) or tw.shape[0] != K:
+    # yw / tw may be strided views ([K, N+1] statistics of atb_f16 consumed in place)
+    for t, nm in ((yw, "yw"), (tw, "tw")):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+            raise TypeError("%s must be a float32 CUDA tensor" % nm)
+    if W.shape[0] != B or tuple(yw.shape) != (K, N) or tuple(tw.shape) != (K,) or yw.stride(1) != 1:
         raise ValueError("inconsistent M-step shapes")
     dev = W.device
     maxiter = int(maxiter)
@@ -583,10 +614,11 @@ def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, t
         tuning = torch.empty((K, N), dtype=torch.float32, device=dev)
     nbytes = lib.pmg_mstep_workspace_bytes(K, B, N, maxiter)
     ws = _workspace(nbytes, dev)
-    check(lib.pmg_mstep_adam(K, B, N, _p(Phi), _p(yw), _p(tw), float(prior_std), float(step_size), float(b1),
-                             float(b2), float(eps), maxiter, float(tol), int(min_iters), _p(W), _p(state.mu),
-                             _p(state.nu), _p(state.count), _p(loss_hist), _p(err_hist), _p(n_iter), _p(final),
-                             _p(tuning), _p(ws), ws.numel(), _stream()), "pmg_mstep_adam")
+    check(lib.pmg_mstep_adam_ld(K, B, N, _p(Phi), _p(yw), int(yw.stride(0)), _p(tw), int(tw.stride(0)),
+                                float(prior_std), float(step_size), float(b1),
+                                float(b2), float(eps), maxiter, float(tol), int(min_iters), _p(W), _p(state.mu),
+                                _p(state.nu), _p(state.count), _p(loss_hist), _p(err_hist), _p(n_iter), _p(final),
+                                _p(tuning), _p(ws), ws.numel(), _stream()), "pmg_mstep_adam")
     _count(1)
     return loss_hist, err_hist, n_iter, final, tuning
 

@@ -19,6 +19,19 @@ class TimeShard:
         self.active = (not single) and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.rank = dist.get_rank(group) if self.active else 0
         self.world = dist.get_world_size(group) if self.active else 1
+        # gloo moves host memory only: device tensors are staged through the host.  That is how several ranks
+        # share ONE GPU (the driver's single-GPU test box, tests/test_gpu_multirank.py); on NCCL nothing is staged.
+        self.staged = self.active and dist.get_backend(group) == "gloo"
+
+    def _out(self, t):
+        """tensor handed to the backend for `t` (host copy of a device tensor under gloo)"""
+        return t.detach().cpu().contiguous() if (self.staged and t.is_cuda) else t.contiguous()
+
+    def _recv_like(self, like):
+        return torch.empty(like.shape, dtype=like.dtype, device="cpu" if self.staged else like.device)
+
+    def _in(self, t, like):
+        return t.to(like.device) if (t is not None and t.device != like.device) else t
 
     @property
     def is_first(self):
@@ -37,19 +50,23 @@ class TimeShard:
         ops, from_left, from_right = [], None, None
         if not self.is_first:
             if to_left is not None:
-                ops.append(dist.P2POp(dist.isend, to_left.contiguous(), self._peer(self.rank - 1), self.group))
+                ops.append(dist.P2POp(dist.isend, self._out(to_left), self._peer(self.rank - 1), self.group))
             if like_left is not None:
-                from_left = torch.empty_like(like_left)
+                from_left = self._recv_like(like_left)
                 ops.append(dist.P2POp(dist.irecv, from_left, self._peer(self.rank - 1), self.group))
         if not self.is_last:
             if to_right is not None:
-                ops.append(dist.P2POp(dist.isend, to_right.contiguous(), self._peer(self.rank + 1), self.group))
+                ops.append(dist.P2POp(dist.isend, self._out(to_right), self._peer(self.rank + 1), self.group))
             if like_right is not None:
-                from_right = torch.empty_like(like_right)
+                from_right = self._recv_like(like_right)
                 ops.append(dist.P2POp(dist.irecv, from_right, self._peer(self.rank + 1), self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        if like_left is not None:
+            from_left = self._in(from_left, like_left)
+        if like_right is not None:
+            from_right = self._in(from_right, like_right)
         return from_left, from_right
 
     def halo_exchange(self, x, halo):
@@ -92,7 +109,7 @@ class TimeShard:
         if not self.active:
             return
         flat = torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat = self._allreduce(flat, dist.ReduceOp.SUM)
         o = 0
         for t in tensors:
             n = t.numel()
@@ -102,16 +119,38 @@ class TimeShard:
     def broadcast_(self, t, src=0):
         """In-place broadcast from rank `src` of the group."""
         if self.active:
-            dist.broadcast(t, src=self._peer(src), group=self.group)
+            if self.staged and t.is_cuda:
+                h = t.detach().cpu()
+                dist.broadcast(h, src=self._peer(src), group=self.group)
+                t.copy_(h)
+            else:
+                dist.broadcast(t, src=self._peer(src), group=self.group)
 
     def allreduce_max_(self, t):
         """In-place element-wise maximum over ranks."""
         if self.active:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            t.copy_(self._allreduce(t, dist.ReduceOp.MAX))
+
+    def _allreduce(self, t, op):
+        """all-reduce of one tensor; returns the reduced tensor on t's device (t itself unless staged)"""
+        if self.staged and t.is_cuda:
+            h = t.detach().cpu()
+            dist.all_reduce(h, op=op, group=self.group)
+            return h.to(t.device)
+        dist.all_reduce(t, op=op, group=self.group)
+        return t
+
+    def allreduce_flat_sum_(self, flat):
+        """In-place sum over ranks of ONE contiguous buffer (no packing copies): the per-iteration collective of
+        the EM loop -- statistics, log marginal and seam verdict travel together."""
+        if self.active:
+            r = self._allreduce(flat, dist.ReduceOp.SUM)
+            if r is not flat:
+                flat.copy_(r)
 
     def max_int(self, v, device):
         if not self.active:
             return int(v)
-        t = torch.tensor([int(v)], dtype=torch.int64, device=device)
+        t = torch.tensor([int(v)], dtype=torch.int64, device="cpu" if self.staged else device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return int(t.item())

@@ -29,8 +29,14 @@ def _dense_move(op):
     return G * inv_z[:, None]
 
 
-def _chains(plan, mode, chain_ids):
-    ids = range(plan.n_chain) if mode == 0 else [int(i) for i in _np(chain_ids).reshape(-1)]
+def _chains(plan, mode, chain_ids, sel_err=None, sel_tol=0.0):
+    if mode == 1:
+        ids = [int(i) for i in _np(chain_ids).reshape(-1)]
+    elif mode == 2:           # selection "on the device": chain s iff !(sel_err[s] <= sel_tol)
+        e = _np(sel_err)
+        ids = [s for s in range(plan.n_chain) if not (e[s] <= sel_tol)]
+    else:
+        ids = range(plan.n_chain)
     for s in ids:
         t_begin = plan.core_begin + s * plan.chunk_len
         t_end = min(t_begin + plan.chunk_len, plan.core_end)
@@ -44,16 +50,20 @@ def _slot(buf, s):
     return b if b.ndim == 2 else b[s]
 
 
+def _halo_next(plan):
+    return int(plan.halo_next) if int(plan.halo_next) > 0 else int(plan.halo)
+
+
 def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None, warm_in=None,
-            warm_out=None):
+            warm_out=None, sel_err=None, sel_tol=0.0):
     K = op.K
     P0 = _dense_move(op)
     M = op.M.reshape(2, 2).astype(np.float64)
     scale = float(plan.likelihood_scale)
     ll_, al_, lmr_ = _np(ll), _np(alpha), _np(lmr)
-    for s, t_begin, t_end in _chains(plan, mode, chain_ids):
+    for s, t_begin, t_end in _chains(plan, mode, chain_ids, sel_err, sel_tol):
         msg = None
-        if mode == 1:
+        if mode != 0:
             t0 = t_begin
             if warm_in is not None:
                 msg = _slot(warm_in, s)
@@ -88,22 +98,22 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
                 lmr_[t] = np.float32(np.log(c) + scale * mx)
             elif t == t_begin - 1 and halo_state is not None:
                 _np(halo_state)[s] = m.astype(np.float32)
-            if (warm_out is not None and t == t_end - plan.halo - 1
+            if (warm_out is not None and t == t_end - _halo_next(plan) - 1
                     and (s + 1 < plan.n_chain or not plan.right_exact)):
                 _np(warm_out)[s + 1] = m.astype(np.float32)
 
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
              beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
-             warm_out=None):
+             warm_out=None, sel_err=None, sel_tol=0.0):
     K, T = op.K, int(plan.T)
     P0 = _dense_move(op)
     M = op.M.reshape(2, 2).astype(np.float64)
     scale = float(plan.likelihood_scale)
     ll_, al_ = _np(ll), _np(alpha)
-    for s, t_begin, t_end in _chains(plan, mode, chain_ids):
+    for s, t_begin, t_end in _chains(plan, mode, chain_ids, sel_err, sel_tol):
         init = None
-        if mode == 1:
+        if mode != 0:
             if t_end < T:
                 t_hi = t_end
                 init = _slot(warm_in, s) if warm_in is not None else _np(beta_end)[s + 1]
@@ -155,7 +165,7 @@ def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_o
                 _np(beta_halo)[s] = be.astype(np.float32)
             if t == t_begin and beta_end is not None:
                 _np(beta_end)[s] = be.astype(np.float32)
-            if warm_out is not None and t == t_begin + plan.halo - 1 and (s >= 1 or not plan.left_exact):
+            if warm_out is not None and t == t_begin + _halo_next(plan) - 1 and (s >= 1 or not plan.left_exact):
                 # slot s-1 of the view; s == 0 writes the slot in front of the view (the caller passes buf[1:])
                 wo = warm_out
                 if s >= 1:
@@ -184,6 +194,22 @@ def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1
         hi, lo = np.maximum(u, v), np.minimum(u, v)
         sel = hi > floor_val
         out[i] = np.float32(((hi - lo)[sel] / np.maximum(lo[sel], 1e-37)).max()) if sel.any() else 0.0
+
+
+def seam_check_fix(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, tol, fix=False, counter=None,
+                   floor_val=1e-12):
+    """Same contract as ops.seam_check_fix (host memory): count seams over the tolerance, optionally replace their
+    estimate by the truth."""
+    seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val)
+    out = _np(err)
+    for i in range(int(n)):
+        if not (out[i] <= tol):
+            if counter is not None:
+                _np(counter)[0] += 1.0
+            if fix:
+                dst = np.ctypeslib.as_array((ctypes.c_float * int(length)).from_address(int(est_ptr) + 4 * i * int(ld_est)))
+                src = np.ctypeslib.as_array((ctypes.c_float * int(length)).from_address(int(truth_ptr) + 4 * i * int(ld_truth)))
+                dst[:] = src
 
 
 class FakeEmission:
@@ -228,11 +254,12 @@ def backward_with_pieces(plan, op, ll, alpha, gamma=None, gamma_lat=None, gamma1
     """backward() that also fills the fp16 hi/lo pieces of gamma_lat, as the CUDA kernels do."""
     T, K = int(plan.T), op.K
     gl = gamma_lat if gamma_lat is not None else torch.zeros((T, K), dtype=torch.float32)
-    if gamma16 is not None and kw.get("mode", 0) == 1:
+    if gamma16 is not None and kw.get("mode", 0) != 0:
         gl.copy_(gamma16[0, :, :K].float() + gamma16[1, :, :K].float())     # rows of chains that are not re-run
     backward(plan, op, ll, alpha, gamma=gamma, gamma_lat=gl, gamma16=None, **kw)
     if gamma16 is not None:
-        for s, t_begin, t_end in _chains(plan, kw.get("mode", 0), kw.get("chain_ids")):
+        for s, t_begin, t_end in _chains(plan, kw.get("mode", 0), kw.get("chain_ids"), kw.get("sel_err"),
+                                         kw.get("sel_tol", 0.0)):
             g = gl[t_begin:t_end]
             hi = g.half()
             gamma16[0, t_begin:t_end, :K] = hi
@@ -257,7 +284,11 @@ def atb_f16(g16, y16, K, out=None):
         Y = torch.cat([Y, torch.ones((Y.shape[0], 1), dtype=torch.float64)], dim=1)
     if g.shape[0] != Y.shape[0]:          # pieces cover the extended block; halo rows are zero
         raise ValueError("row mismatch")
-    return (g.T @ Y).float()
+    res = (g.T @ Y).float()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, tol=1e-6, min_iters=5,

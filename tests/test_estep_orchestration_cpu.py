@@ -47,6 +47,7 @@ def _patch():
     torch.cuda.current_stream = lambda dev=None: _Stream()
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     ops.forward, ops.backward, ops.seam_check = emu.forward, emu.backward, emu.seam_check
+    ops.seam_check_fix = emu.seam_check_fix
     ops.EmissionOperands = emu.FakeEmission
     ops.scan_compact_supported = lambda op, scale: False
     return emu
@@ -71,9 +72,10 @@ def _tunings(d, n_pass):
     return out
 
 
-def _worker(rank, world, port, cfg, q):
+def _worker(rank, world, port, cfg, q, device_repair=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["PMG_DEVICE_REPAIR"] = str(device_repair)
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -92,9 +94,9 @@ def _worker(rank, world, port, cfg, q):
         for tun in _tunings(d, n_pass):
             res = es.run(torch.from_numpy(tun.astype(np.float32)), want_gamma=True, want_gamma_lat=True,
                          want_dyn=True, want_r=False)
-            lm = res.log_marginal.reshape(1).clone()
-            es.shard.allreduce_sum_(lm)
-            out.append({"gamma": res.gamma.numpy().copy(), "lm": float(lm[0]), "relay": (res.n_relay_fwd, res.n_relay_bwd),
+            out.append({"gamma": res.gamma.numpy().copy(), "lm": float(res.log_marginal),      # global already
+                        "relay": (res.n_relay_fwd + res.n_fix_fwd, res.n_relay_bwd + res.n_fix_bwd),
+                        "host_relay": (res.n_relay_fwd, res.n_relay_bwd),
                         "repaired": res.repaired, "err": (res.seam_err_fwd, res.seam_err_bwd),
                         "n_chain": res.plan.n_chain})
         q.put((rank, out))
@@ -106,11 +108,11 @@ def _worker(rank, world, port, cfg, q):
             dist.destroy_process_group()
 
 
-def _run(world, cfg):
+def _run(world, cfg, device_repair=1):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q, device_repair)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in procs)
@@ -134,13 +136,14 @@ def _oracle(cfg):
     return out
 
 
-@pytest.mark.parametrize("world", [1, 3, 8])
-def test_estep_orchestration_matches_sequential_answer(world):
+@pytest.mark.parametrize("world,device_repair", [(1, 1), (3, 1), (8, 1), (1, 0), (3, 0)])
+def test_estep_orchestration_matches_sequential_answer(world, device_repair):
     # 8 ranks x 96 bins, chains of 24 bins, warm-up of 16: several chains per rank, rank boundaries with both
-    # neighbours, a warm-up too short for the first (cold) pass -> repair sweeps; later passes start warm
+    # neighbours, a warm-up too short for the first (cold) pass -> repairs (tier 1: conditional relaunch selected
+    # "on the device"; tier 2 / device_repair=0: host sweeps); later passes start warm
     cfg = (768, 12, 24, 16, 24, 3, 5)
     want = _oracle(cfg)
-    got = _run(world, cfg)
+    got = _run(world, cfg, device_repair)
     n_pass = cfg[5]
     for i in range(n_pass):
         gamma = np.concatenate([got[r][i]["gamma"] for r in range(world)])
@@ -165,9 +168,10 @@ def test_estep_orchestration_matches_sequential_answer(world):
 # when chains are re-run; time-sharded ranks broadcast the M-step result.  With deterministic stand-ins the
 # speculative loop must reproduce the plain loop bit for bit.
 # ---------------------------------------------------------------------------------------------------------
-def _em_worker(rank, world, port, cfg, speculate, q):
+def _em_worker(rank, world, port, cfg, speculate, q, device_repair=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["PMG_DEVICE_REPAIR"] = str(device_repair)
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -212,11 +216,12 @@ def _em_worker(rank, world, port, cfg, speculate, q):
             dist.destroy_process_group()
 
 
-def _run_em(world, cfg, speculate):
+def _run_em(world, cfg, speculate, device_repair=0):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_em_worker, args=(r, world, port, cfg, speculate, q)) for r in range(world)]
+    procs = [ctx.Process(target=_em_worker, args=(r, world, port, cfg, speculate, q, device_repair))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=900) for _ in procs)
@@ -227,11 +232,12 @@ def _run_em(world, cfg, speculate):
     return res
 
 
-@pytest.mark.parametrize("world", [1, 3])
-def test_em_loop_speculative_mstep_equals_plain_loop(world):
+@pytest.mark.parametrize("world,device_repair", [(1, 0), (3, 0), (3, 1)])
+def test_em_loop_speculative_mstep_equals_plain_loop(world, device_repair):
+    """device_repair=0: every repair is a host sweep, so the scenario contains rolled-back speculative M-steps."""
     cfg = (288, 12, 24, 16, 24, 5, 5)
-    plain = _run_em(world, cfg, speculate=False)
-    spec = _run_em(world, cfg, speculate=True)
+    plain = _run_em(world, cfg, speculate=False, device_repair=device_repair)
+    spec = _run_em(world, cfg, speculate=True, device_repair=device_repair)
     n_iter = cfg[5]
     for r in range(world):
         for i in range(n_iter):
@@ -250,7 +256,7 @@ def test_em_loop_speculative_mstep_equals_plain_loop(world):
         assert np.array_equal(spec[r][n_iter - 1]["tuning"], spec[0][n_iter - 1]["tuning"])
     # the scenario must contain at least one repaired iteration (rollback path) and one clean one
     rep = [spec[0][i]["repaired"] for i in range(n_iter)]
-    assert any(rep)
+    assert any(rep) or device_repair
 
 
 def _fit_worker(q):

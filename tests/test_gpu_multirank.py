@@ -1,4 +1,8 @@
-"""Two-GPU check of the time-sharded EM path against the single-GPU run (needs >= 2 CUDA devices)."""
+"""Time-sharded EM path against the single-GPU run.  With >= `world` CUDA devices the ranks use one GPU each over
+NCCL; on a smaller box (the driver's test box has ONE GPU) the same ranks share cuda:0 and exchange through gloo
+(`TimeShard` stages device tensors through the host there), so the sharded orchestration -- boundary messages, halo
+rows, warm starts across rank boundaries, the packed statistics all-reduce, the replicated M-step -- runs on the real
+kernels either way."""
 import os
 import socket
 
@@ -30,16 +34,20 @@ def _fit(y, lp0, params, basis_ls, N, K, device, **kw):
     return res, dec
 
 
-def _worker(rank, world, port, y, lp0, params, N, K, q):
+def _worker(rank, world, port, y, lp0, params, N, K, q, nccl):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank if nccl else 0)
+    torch.cuda.set_device(dev)
+    if nccl:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         T = y.shape[0]
         lo, hi = rank * T // world, (rank + 1) * T // world
-        res, dec = _fit(y[lo:hi], lp0[lo:hi], params, 8.0, N, K, torch.device("cuda", rank), time_sharded=True)
+        res, dec = _fit(y[lo:hi], lp0[lo:hi], params, 8.0, N, K, dev, time_sharded=True)
         q.put((rank, {"lml": np.array(res["log_marginal_l"]), "tuning": res["tuning"],
                       "post": res["posterior_latent_marg"], "dyn": res["posterior_dynamics_marg"],
                       "dec_lml": dec["log_marginal_final"], "dec_post": dec["posterior_latent_marg"],
@@ -51,11 +59,10 @@ def _worker(rank, world, port, y, lp0, params, N, K, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_time_sharded_fit_matches_single_gpu(world):
-    """world = 4 exercises interior ranks (two neighbours, both boundary exchanges)."""
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+    """world >= 3 exercises interior ranks (two neighbours, both boundary exchanges)."""
+    nccl = torch.cuda.device_count() >= world
     import poor_man_gplvm_b200 as pmg
     N, K, T = 30, 96, 6000
     d = make_dataset(T, N, K, seed=21)
@@ -68,7 +75,7 @@ def test_time_sharded_fit_matches_single_gpu(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, d["y"], lp0, params, N, K, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, d["y"], lp0, params, N, K, q, nccl)) for r in range(world)]
     for p in procs:
         p.start()
     out = dict(q.get(timeout=600) for _ in procs)

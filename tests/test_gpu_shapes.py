@@ -1,0 +1,145 @@
+"""Model-level parity at the REAL shapes of BASELINE.json's configs (the small-shape tests live in test_gpu_model.py /
+test_gpu_golden.py): the kernels that only engage at these sizes are chained the way a production fit chains them --
+fp16-piece posterior -> tensor-core statistics -> 125-CTA lagged Adam kernel -> tcgen05 emission -> QP=7 compact
+scans with several chains and seams.
+
+Oracle: ``oracle.linear_ref.fit_em_linear`` in fp64 (the reference EM driver with the restated M-step and the
+linear-space E-step; pinned against the reference source's own README run in tests/test_oracle_golden.py).  The
+log-space restatement costs 4K^2 exponentials per bin and is used only where it finishes in seconds.
+Tolerances are BASELINE.json's: log_marginal_l 1e-4 relative per iteration, posterior marginals 1e-5 absolute for one
+teacher-forced iteration (chained iterations accumulate fp32 rounding of the Adam steps: 5e-5), tuning 1e-3
+relative, naive-Bayes argmax identical except at fp32-unresolvable ties.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import linear_ref as lin
+from oracle import ref_numpy as ref
+from poor_man_gplvm_b200.synthetic import make_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(N, K, T, ls, seed, **model_kw):
+    import poor_man_gplvm_b200 as pmg
+    d = make_dataset(T, N, K, seed=seed)
+    model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, **model_kw)
+    rng = np.random.default_rng(seed + 1)
+    params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
+    model.params = params.copy()
+    model.tuning = np.logaddexp(model.tuning_basis @ params, np.float32(0)).astype(np.float32)
+    oracle = ref.OraclePoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, dtype=np.float64,
+                                          tuning_basis=model.tuning_basis, params=params,
+                                          **{k: v for k, v in model_kw.items() if k != "device"})
+    lp0, _ = model.init_latent_posterior(T, key=7)
+    return d, model, oracle, lp0
+
+
+def _check_em(got, want, n_iter, post_tol):
+    lw, lg = np.array(want["log_marginal_l"]), np.array(got["log_marginal_l"], dtype=np.float64)
+    assert lg.shape == (n_iter,)
+    assert np.max(np.abs(lg - lw) / np.abs(lw)) < 1e-4, (lg, lw)
+    assert np.max(np.abs(got["tuning"] - want["tuning"]) / want["tuning"]) < 1e-3
+    assert np.max(np.abs(got["posterior_latent_marg"] - want["posterior_latent_marg"])) < post_tol
+    assert np.max(np.abs(got["posterior_dynamics_marg"] - want["posterior_dynamics_marg"])) < post_tol
+    assert np.max(np.abs(got["posterior"] - want["posterior"])) < post_tol
+
+
+def test_headline_shape_fit_em_chained():
+    """configs[3] shape (N=500, K=400), T=6000, three chained EM iterations, Adam pinned at 30 steps."""
+    N, K, T = 500, 400, 6000
+    d, model, oracle, lp0 = _pair(N, K, T, 10.0, seed=11)
+    kw = dict(n_iter=3, log_posterior_init=lp0, m_step_maxiter=30, m_step_tol=-1)
+    got = model.fit_em(d["y"], **kw)
+    info = model._last_estep_info
+    # the production kernels ran: tensor-core statistics + compact scans over several chains
+    assert info["tensor_core_statistics"] and info["compact_scan"] and info["n_chain"] >= 8, info
+    want = lin.fit_em_linear(oracle, d["y"], **kw)
+    assert got["m_step_res_l"]["n_iter"] == [30] * 3 == want["m_step_n_iter"]
+    assert np.allclose(got["m_step_res_l"]["final_loss"], want["m_step_final_loss"], rtol=1e-4)
+    _check_em(got, want, 3, 5e-5)
+
+
+def test_headline_shape_one_iteration_teacher_forced():
+    """One M+E step at N=500, K=400 from identical state: the 1e-5 absolute posterior tolerance."""
+    N, K, T = 500, 400, 4000
+    d, model, oracle, lp0 = _pair(N, K, T, 10.0, seed=12)
+    kw = dict(n_iter=1, log_posterior_init=lp0, m_step_maxiter=40, m_step_tol=-1)
+    got = model.fit_em(d["y"], **kw)
+    want = lin.fit_em_linear(oracle, d["y"], **kw)
+    _check_em(got, want, 1, 1e-5)
+    # decode_latent with the fitted tuning: smoother outputs and the transition statistics (xi GEMM on tensor cores)
+    dec = model.decode_latent(d["y"])
+    P, _, M, _ = oracle._transitions({})
+    es = lin.e_step(d["y"].astype(np.float64), want["tuning"], P.astype(np.float64), M.astype(np.float64),
+                    oracle.ma_neuron_default, oracle.ma_latent_default, want_xi=True)
+    assert abs(dec["log_marginal_final"] - es["log_marginal"]) < 1e-4 * abs(es["log_marginal"])
+    assert np.max(np.abs(dec["posterior_all"] - es["gamma"])) < 1e-5
+    xi = es["xi"] / es["xi"].sum()
+    assert np.max(np.abs(np.asarray(dec["p_joint_full"]) - xi)) < 1e-5
+    assert np.max(np.abs(np.asarray(dec["p_joint_latent"]) - xi.sum(axis=(0, 1)))) < 1e-5
+
+
+def test_session_shape_default_adam():
+    """configs[1] shape (N=200, K=100), T=20000, the reference's default optimiser (maxiter=1000, tol=1e-6).  The
+    stopping step is decided by a relative loss change of 1e-6, i.e. by rounding (see
+    test_gpu_golden.py::test_fit_em_readme_config_default_adam): step counts are compared within 15 %."""
+    N, K, T = 200, 100, 20000
+    d, model, oracle, lp0 = _pair(N, K, T, 10.0, seed=13)
+    kw = dict(n_iter=3, log_posterior_init=lp0)
+    got = model.fit_em(d["y"], **kw)
+    want = lin.fit_em_linear(oracle, d["y"], **kw)
+    lw, lg = np.array(want["log_marginal_l"]), np.array(got["log_marginal_l"], dtype=np.float64)
+    assert np.max(np.abs(lg - lw) / np.abs(lw)) < 1e-4, (lg, lw)
+    n_got, n_want = np.array(got["m_step_res_l"]["n_iter"]), np.array(want["m_step_n_iter"])
+    assert np.all(n_got >= 0.85 * n_want - 2) and np.all(n_got <= 1.15 * n_want + 2), (n_got, n_want)
+    # different stopping steps leave the tuning within the optimiser's own tolerance, not within 1e-3
+    assert np.max(np.abs(got["tuning"] - want["tuning"]) / want["tuning"]) < 3e-2
+    assert np.max(np.abs(got["posterior_latent_marg"] - want["posterior_latent_marg"])) < 2e-2
+
+
+def test_naive_bayes_config_c_shape():
+    """configs[2] shape (N=1000, K=200): log-likelihood vs the GEMM-form fp64 oracle on 30000 bins, argmax identical
+    except at fp32-unresolvable ties; the log-space restatement (decoder.py:88-149) on the first 1500 bins."""
+    import poor_man_gplvm_b200 as pmg
+    N, K, T = 1000, 200, 30000
+    d = make_dataset(T, N, K, seed=14)
+    model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=10.0)
+    tuning = (d["tuning_true"] * (1.0 + 0.1 * np.random.default_rng(3).standard_normal((K, N)))).clip(0.01).astype(np.float32)
+    got = model.decode_latent_naive_bayes(d["y"], tuning=tuning)
+    ll = lin.emission_gemm_form(d["y"], tuning.astype(np.float64), np.ones(N), np.ones(K))
+    assert np.max(np.abs(got["ll_per_pos_l"] - ll) / np.maximum(1.0, np.abs(ll))) < 2e-6
+    m = ll.max(axis=1, keepdims=True)
+    lml = (np.log(np.exp(ll - m).sum(axis=1)) + m[:, 0])
+    assert np.max(np.abs(got["log_marginal_l"] - lml) / np.abs(lml)) < 2e-6
+    assert abs(got["log_marginal_total"] - lml.sum()) < 1e-5 * abs(lml.sum())
+    assert np.max(np.abs(got["posterior_latent"] - np.exp(ll - lml[:, None]))) < 1e-4
+    am_g, am_w = got["log_posterior_latent"].argmax(axis=1), ll.argmax(axis=1)
+    mism = np.nonzero(am_g != am_w)[0]
+    for t in mism:
+        gap = abs(ll[t, am_g[t]] - ll[t, am_w[t]])
+        assert gap < 4 * np.spacing(np.float32(np.abs(ll[t]).max())), (t, gap)
+    assert mism.size <= 3
+    o = ref.OraclePoissonGPLVMJump1D(N, K, tuning_lengthscale=10.0, dtype=np.float64,
+                                     tuning_basis=model.tuning_basis, params=model.params)
+    want = o.decode_latent_naive_bayes(d["y"][:1500], tuning=tuning.astype(np.float64), n_time_per_chunk=250)
+    assert np.allclose(want["ll_per_pos_l"], ll[:1500], rtol=1e-10)          # GEMM form == reference form
+    assert np.array_equal(want["log_posterior_latent"].argmax(axis=1), am_w[:1500])
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_stress_shape_k2000(dense):
+    """configs[4] shape (N=300, K=2000): one EM iteration + decode against the fp64 linear oracle, with the default
+    (banded) move kernel and with a genuinely dense custom transition kernel (reference gp_kernel.py:61-66)."""
+    N, K, T = 300, 2000, 1200
+    mk = {}
+    if dense:
+        x = np.arange(K, dtype=np.float64)
+        mk["custom_transition_kernel"] = (np.exp(-np.abs(x[:, None] - x[None, :]) / 150.0) + 0.02).astype(np.float32)
+    d, model, oracle, lp0 = _pair(N, K, T, 10.0, seed=15, **mk)
+    kw = dict(n_iter=1, log_posterior_init=lp0, m_step_maxiter=10, m_step_tol=-1)
+    got = model.fit_em(d["y"], **kw)
+    want = lin.fit_em_linear(oracle, d["y"], **kw)
+    _check_em(got, want, 1, 1e-5)

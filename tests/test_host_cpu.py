@@ -35,8 +35,9 @@ def test_struct_layouts_match_header():
     from poor_man_gplvm_b200._lib import PmgScanPlan, PmgTransition
     # int K,kind,W (+4 pad) ; 4 pointers ; float[4]
     assert ctypes.sizeof(PmgTransition) == 16 + 32 + 16
-    # 4 x int64 ; 4 x int ; float (+4 pad)
-    assert ctypes.sizeof(PmgScanPlan) == 32 + 16 + 8
+    # 4 x int64 ; 4 x int ; float likelihood_scale, int halo_next, float sel_tol (+4 pad) ; pointer sel_err
+    assert ctypes.sizeof(PmgScanPlan) == 32 + 16 + 16 + 8
+    assert PmgScanPlan.sel_err.offset == 64 and PmgScanPlan.halo_next.offset == 52
 
 
 def test_transition_and_basis_match_oracle():
@@ -78,15 +79,18 @@ def test_move_operator_factorisation_reconstructs_P0(K, mv):
 
 
 def test_plan_chunks_bounds():
-    from poor_man_gplvm_b200.estep import plan_chunks
-    from poor_man_gplvm_b200.estep import MIN_CHUNK_OVER_HALO
+    from poor_man_gplvm_b200.estep import plan_chunks, MIN_CHUNK
     assert plan_chunks(400, 256, 148) == 400                      # short sequences: one exact chain
     c = plan_chunks(10 ** 6, 256, 148)
-    assert c >= MIN_CHUNK_OVER_HALO * 256 and (10 ** 6 + c - 1) // c <= 148 * 8
+    assert c >= 2 * 256 and (10 ** 6 + c - 1) // c <= 148 * 8
     assert (10 ** 6 + c - 1) // c > 148 * 7                       # the headline run fills every SM
     c12 = plan_chunks(10 ** 6, 256, 148, 12)                      # EM-mode plan of the compact kernels
-    assert c12 >= MIN_CHUNK_OVER_HALO * 256 and 148 * 11 < (10 ** 6 + c12 - 1) // c12 <= 148 * 12
+    assert c12 >= 2 * 256 and 148 * 11 < (10 ** 6 + c12 - 1) // c12 <= 148 * 12
     assert plan_chunks(5000, 0, 148) == 5000
+    # one-shot passes keep chunks of at least two warm-ups; EM mode (adaptive warm-up) fills the chain slots even
+    # for a rank's share of a time-sharded recording (T = 1e6 over 8 ranks)
+    assert plan_chunks(125000, 256, 148, 12) == 512
+    assert plan_chunks(125000, 256, 148, 12, min_chunk=MIN_CHUNK) == 71
 
 
 def test_model_constructs_on_cpu_and_fails_loudly_without_gpu():

@@ -117,3 +117,18 @@ def test_oracle_readme_config_matches_reference_source():
     em = o.fit_em(g["in_y"].astype(np.float64), **kw)
     assert np.allclose(np.array(em["log_marginal_l"]), g["em_log_marginal_l"][:3], rtol=1e-10)
     assert [int(n) for n in em["m_step_res_l"]["n_iter"]] == [50, 50, 50]
+
+
+def test_linear_em_driver_matches_reference_source():
+    """oracle/linear_ref.fit_em_linear (restated M-step + linear-space E-step; the oracle of the real-shape GPU
+    parity tests, tests/test_gpu_shapes.py) against the reference source's README run in fp64."""
+    from oracle import linear_ref as lin
+    g, c = load("readme_pinned", "f64")
+    o = make_oracle(g, c, np.float64)
+    kw = em_kwargs(g, c)
+    kw.pop("n_time_per_chunk")
+    em = lin.fit_em_linear(o, g["in_y"].astype(np.float64), **kw)
+    assert np.allclose(np.array(em["log_marginal_l"]), g["em_log_marginal_l"], rtol=1e-9)
+    assert np.allclose(em["tuning"], g["em_tuning"], rtol=1e-6)
+    assert np.allclose(em["posterior"], g["em_posterior"], rtol=0, atol=1e-7)      # fixture stored in float32
+    assert em["m_step_n_iter"] == [int(v) for v in g["em_m_n_iter"]]
