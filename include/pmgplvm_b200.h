@@ -126,6 +126,8 @@ typedef struct pmg_scan_plan {
   int halo_next;      /* warm-up length of the NEXT pass (where warm_out messages are taken); 0 = halo */
   float sel_tol;      /* mode 2: chain s is re-run iff !(sel_err[s] <= sel_tol) */
   const float* sel_err; /* mode 2: device array [n_chain] of seam errors (pmg_seam_check_fix) */
+  const int* halo_arr;      /* optional device int32 [n_chain]: per-chain warm-up lengths of this pass (overrides halo) */
+  const int* halo_next_arr; /* optional device int32 [n_chain]: per-chain warm-up lengths of the next pass */
 } pmg_scan_plan;
 
 /* mode 0: all chains, warm-up from the uniform carry (left-most chain exact if left_exact).

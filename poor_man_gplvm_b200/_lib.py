@@ -28,7 +28,7 @@ class PmgScanPlan(C.Structure):
                 ("chunk_len", C.c_int64), ("n_chain", C.c_int), ("halo", C.c_int),
                 ("left_exact", C.c_int), ("right_exact", C.c_int),
                 ("likelihood_scale", C.c_float), ("halo_next", C.c_int), ("sel_tol", C.c_float),
-                ("sel_err", C.c_void_p)]
+                ("sel_err", C.c_void_p), ("halo_arr", C.c_void_p), ("halo_next_arr", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/pmgplvm_b200.h

@@ -29,6 +29,8 @@ struct ScanCommon {
   int64_t T, core_begin, core_end, chunk_len;
   int n_chain, halo, left_exact, right_exact;
   int halo_next;            // warm-up length of the NEXT pass: where warm_out messages are taken
+  const int* halo_arr;      // optional per-chain warm-up lengths of this pass (overrides halo) ...
+  const int* halo_next_arr; // ... and of the next pass (overrides halo_next for chains of this block)
   const float* sel_err;     // mode 2: chain s runs iff !(sel_err[s] <= sel_tol)
   float sel_tol;
   float scale;
@@ -39,6 +41,22 @@ struct ScanCommon {
   const int* chain_ids;
   int n_ids;
 };
+
+__device__ __forceinline__ int halo_own(const ScanCommon& c, int s) { return c.halo_arr ? c.halo_arr[s] : c.halo; }
+// warm-up length chain j will use in the next pass (j outside this block: the neighbour rank's boundary chain)
+__device__ __forceinline__ int halo_next_of(const ScanCommon& c, int j) {
+  return (c.halo_next_arr && j >= 0 && j < c.n_chain) ? c.halo_next_arr[j] : c.halo_next;
+}
+// mode 2: true when none of this CTA's chains is selected (the CTA returns before touching shared memory)
+__device__ __forceinline__ bool cta_idle(const ScanCommon& c, int chains_per_cta) {
+  if (c.mode != 2) return false;
+  int any = 0;
+  for (int j = threadIdx.x; j < chains_per_cta; j += blockDim.x) {
+    const int s = blockIdx.x * chains_per_cta + j;
+    if (s < c.n_chain && !(c.sel_err[s] <= c.sel_tol)) any = 1;
+  }
+  return __syncthreads_or(any) == 0;
+}
 
 struct FwdParams {
   ScanCommon c;
@@ -218,6 +236,7 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
   using Ge = Geo<Q, WPC, WT>;
   extern __shared__ float smem[];
   const ScanCommon& c = p.c;
+  if (cta_idle(c, Geo<Q, WPC, WT>::CPC)) return;
   const int K = c.tr.K, W = c.tr.W, kind = c.tr.kind;
   const int grp = threadIdx.x / Ge::G;
   const int gl = threadIdx.x % Ge::G;
@@ -271,7 +290,7 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
     else if (t0 > 0) { from_array = true; src = p.alpha + (size_t)(t0 - 1) * 2 * K; }
     else if (p.carry_in) { from_array = true; src = p.carry_in; }
   } else {
-    t0 = cr.t_begin - c.halo;
+    t0 = cr.t_begin - halo_own(c, cr.s);
     if (t0 <= 0 && c.left_exact) {
       t0 = 0;
       if (p.carry_in) { from_array = true; src = p.carry_in; }
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(256, 1) fwd_kernel(const FwdParams p) {
         }
       }
     }
-    if (p.warm_out && t == cr.t_end - c.halo_next - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
+    if (p.warm_out && t == cr.t_end - halo_next_of(c, cr.s + 1) - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
       float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -404,6 +423,7 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
   using Ge = Geo<Q, WPC, WT>;
   extern __shared__ float smem[];
   const ScanCommon& c = p.c;
+  if (cta_idle(c, Geo<Q, WPC, WT>::CPC)) return;
   const int K = c.tr.K, W = c.tr.W, kind = c.tr.kind;
   const int grp = threadIdx.x / Ge::G;
   const int gl = threadIdx.x % Ge::G;
@@ -455,7 +475,7 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
       init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
     } else { t_hi = c.T - 1; init = p.beta_in; }
   } else {
-    t_hi = cr.t_end - 1 + c.halo;
+    t_hi = cr.t_end - 1 + halo_own(c, cr.s);
     if (t_hi >= c.T - 1 && c.right_exact) {
       t_hi = c.T - 1;
       init = p.beta_in;
@@ -617,7 +637,7 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
         }
       }
     }
-    if (p.warm_out && t == cr.t_begin + c.halo_next - 1 && (cr.s >= 1 || !c.left_exact)) {
+    if (p.warm_out && t == cr.t_begin + halo_next_of(c, cr.s - 1) - 1 && (cr.s >= 1 || !c.left_exact)) {
       float* o = p.warm_out + ((int64_t)cr.s - 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -801,6 +821,7 @@ static int fill_common(ScanCommon& c, const pmg_scan_plan* plan, const pmg_trans
   c.chunk_len = plan->chunk_len; c.n_chain = plan->n_chain; c.halo = plan->halo;
   c.halo_next = plan->halo_next > 0 ? plan->halo_next : plan->halo;
   c.sel_err = plan->sel_err; c.sel_tol = plan->sel_tol;
+  c.halo_arr = plan->halo_arr; c.halo_next_arr = plan->halo_next_arr;
   c.left_exact = plan->left_exact; c.right_exact = plan->right_exact;
   c.scale = plan->likelihood_scale;
   c.tr.K = tr->K; c.tr.kind = tr->kind; c.tr.W = tr->W;

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
   constexpr int KP = BG::KP;
   extern __shared__ __align__(16) float smem[];
   const ScanCommon& c = p.c;
+  if (cta_idle(c, NW)) return;
   const int K = c.tr.K, W = c.tr.W;
   const int grp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
     else if (t0 > 0) src = p.alpha + (size_t)(t0 - 1) * 2 * K;
     else if (p.carry_in) src = p.carry_in;
   } else {
-    t0 = cr.t_begin - c.halo;
+    t0 = cr.t_begin - halo_own(c, cr.s);
     if (t0 <= 0 && c.left_exact) {
       t0 = 0;
       if (p.carry_in) src = p.carry_in;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_bulk_kernel(const FwdParams p,
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = v0[q] * inv_prev; o[K + x0 + q] = v1[q] * inv_prev; }
     }
-    if (p.warm_out && t == cr.t_end - c.halo_next - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
+    if (p.warm_out && t == cr.t_end - halo_next_of(c, cr.s + 1) - 1 && (cr.s + 1 < c.n_chain || !c.right_exact)) {
       float* o = p.warm_out + (size_t)(cr.s + 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q)
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
   constexpr int KP = BG::KP;
   extern __shared__ __align__(16) float smem[];
   const ScanCommon& c = p.c;
+  if (cta_idle(c, NW)) return;
   const int K = c.tr.K, W = c.tr.W;
   const int grp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
       init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
     } else { t_hi = c.T - 1; init = p.beta_in; }
   } else {
-    t_hi = cr.t_end - 1 + c.halo;
+    t_hi = cr.t_end - 1 + halo_own(c, cr.s);
     if (t_hi >= c.T - 1 && c.right_exact) {
       t_hi = c.T - 1;
       init = p.beta_in;
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
       for (int q = 0; q < Q; ++q)
         if (x0 + q < K) { o[x0 + q] = b0[q] * inv; o[K + x0 + q] = b1[q] * inv; }
     }
-    if (p.warm_out && t == cr.t_begin + c.halo_next - 1 && (cr.s >= 1 || !c.left_exact)) {
+    if (p.warm_out && t == cr.t_begin + halo_next_of(c, cr.s - 1) - 1 && (cr.s >= 1 || !c.left_exact)) {
       float* o = p.warm_out + ((int64_t)cr.s - 1) * 2 * K;
 #pragma unroll
       for (int q = 0; q < Q; ++q)

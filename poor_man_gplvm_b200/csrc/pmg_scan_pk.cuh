@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   constexpr int Q = G::Q, KP = G::KP;
   extern __shared__ __align__(16) float smem[];
   const ScanCommon& c = p.c;
+  if (cta_idle(c, NW)) return;
   const int K = c.tr.K, W = c.tr.W;
   const int grp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
     if (p.warm_in) src = p.warm_in + (size_t)cr.s * p.warm_stride;
     else if (t0 == 0 && p.carry_in) src = p.carry_in;
   } else {
-    t0 = cr.t_begin - c.halo;
+    t0 = cr.t_begin - halo_own(c, cr.s);
     if (t0 <= 0 && c.left_exact) {
       t0 = 0;
       if (p.carry_in) src = p.carry_in;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
   const int n_steps = (int)(cr.t_end - t0);
   const int i_begin = (int)(cr.t_begin - t0);                    // first bin whose row is stored
   const int e_halo = p.halo_state ? i_begin - 1 : -1;            // warmed-up message in front of the chain
-  const int e_warm = (p.warm_out && (cr.s + 1 < c.n_chain || !c.right_exact)) ? (int)(cr.t_end - c.halo_next - 1 - t0) : -1;
+  const int e_warm = (p.warm_out && (cr.s + 1 < c.n_chain || !c.right_exact)) ? (int)(cr.t_end - halo_next_of(c, cr.s + 1) - 1 - t0) : -1;
   const int e_end = p.fwd_end ? n_steps - 1 : -1;
   const int e_first = (p.first_out && cr.t_begin == c.core_begin) ? i_begin : -1;
   int evt = next_event(-1, e_halo, e_warm, e_end, e_first);
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
   constexpr int SLOT = G::BWD_SLOT;
   extern __shared__ __align__(16) float smem[];
   const ScanCommon& c = p.c;
+  if (cta_idle(c, NW)) return;
   const int K = c.tr.K, W = c.tr.W;
   const int grp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
       init = p.warm_in ? p.warm_in + (size_t)cr.s * p.warm_stride : p.beta_end + (size_t)(cr.s + 1) * 2 * K;
     } else { t_hi = c.T - 1; init = p.beta_in; }
   } else {
-    t_hi = cr.t_end - 1 + c.halo;
+    t_hi = cr.t_end - 1 + halo_own(c, cr.s);
     if (t_hi >= c.T - 1 && c.right_exact) {
       t_hi = c.T - 1;
       init = p.beta_in;
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
   const int i_core = (int)(t_hi - (cr.t_end - 1));               // first step of the chain's own bins
   const int e_halo = (p.beta_halo && i_alpha >= 0) ? i_alpha : -1;          // t == t_end
   const int e_end = p.beta_end ? n_steps - 1 : -1;                          // t == t_begin
-  const int e_warm = (p.warm_out && (cr.s >= 1 || !c.left_exact)) ? (int)(t_hi - (cr.t_begin + c.halo_next - 1)) : -1;
+  const int e_warm = (p.warm_out && (cr.s >= 1 || !c.left_exact)) ? (int)(t_hi - (cr.t_begin + halo_next_of(c, cr.s - 1) - 1)) : -1;
   int evt = next_event(-1, e_halo, e_end, e_warm, -1);
 
   const uint32_t row_bytes = (uint32_t)K * 4;

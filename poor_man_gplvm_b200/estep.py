@@ -109,9 +109,9 @@ class EStep:
             chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count, EM_CHAINS_PER_SM if wide else 8,
                                     min_chunk=(min(MIN_CHUNK, 2 * self.halo) if self.adaptive else None))
         self.chunk_len = int(min(max(1, chunk_len), self.T_core))
-        # warm-up of this pass and of the next one (the pass writes the next pass's warm-start messages)
+        # common warm-up of this pass and of the next one (the pass writes the next pass's warm-start messages)
         self.halos = [self.halo, self.halo]
-        self._calm, self._hold = 0, 0
+        self._calm = 0
         self.plan = ops.make_plan(self.T, self.core.start, self.core.stop, self.chunk_len, self.halo,
                                   self.shard.is_first, self.shard.is_last, self.scale, halo_next=self.halo)
         S = self.plan.n_chain
@@ -159,8 +159,23 @@ class EStep:
             buf[S] = 1.0
         self.warm_cur = 0
         self.warm_valid = False
-        self.err = torch.zeros(2 * S, **f32)
+        self.err = torch.zeros(2 * S, **f32)                       # final check of every seam
+        self.err1 = torch.zeros(2 * S, **f32)                      # first check of the interior seams (before repairs)
         self.err_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
+        self.err1_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
+        # per-chain warm-up lengths (adaptive mode): [this pass, next pass] for each direction, device + host copies
+        self.hf = self.hb = None
+        if self.adaptive:
+            import numpy as np
+            i32 = dict(dtype=torch.int32, device=self.dev)
+            self.hf = [torch.full((S,), self.halo, **i32), torch.full((S,), self.halo, **i32)]
+            self.hb = [torch.full((S,), self.halo, **i32), torch.full((S,), self.halo, **i32)]
+            self.hf_host = [np.full(S, self.halo, np.int32), np.full(S, self.halo, np.int32)]
+            self.hb_host = [np.full(S, self.halo, np.int32), np.full(S, self.halo, np.int32)]
+            self.boost_f, self.boost_b = np.zeros(S, np.int32), np.zeros(S, np.int32)
+            self.h_cur = 0
+            # a boosted warm-up still starts inside the previous chain's processed bins (or the fetched halo rows)
+            self.boost_cap = max(self.halo, min(4 * self.halo, self.chunk_len + self.halo_min))
         self.tail = tail if tail is not None else torch.zeros(TAIL, **f32)
         if self.tail.numel() != TAIL or self.tail.dtype != torch.float32 or not self.tail.is_contiguous():
             raise ValueError("tail must be a contiguous float32 view of %d entries" % TAIL)
@@ -247,32 +262,34 @@ class EStep:
             if nxt is not None:
                 self.bwarm[nxt][self.S].copy_(from_right[K2:].view(2, self.K))
 
-    def _check_fwd(self, compact, lo, fix, counter):
+    def _check_fwd(self, compact, lo, fix, counter, err=None):
         """Forward seams lo..S-1 (seam c sits in front of chain c): warmed-up estimate vs the true message.
         fix: failed estimates are replaced by the truth (the snapshot a mode-2 restart starts from)."""
         S, K2 = self.S, 2 * self.K
         if lo >= S:
             return
+        err = self.err if err is None else err
         est = self.halo_state
         if compact:
             ops.seam_check_fix(S - lo, K2, est[lo].data_ptr(), K2, self.fwd_end_ext[lo].data_ptr(), K2,
-                               self.err[lo:S], self.seam_tol, fix, counter)
+                               err[lo:S], self.seam_tol, fix, counter)
             return
         if lo == 0:         # the left neighbour rank's message
-            ops.seam_check_fix(1, K2, est[0].data_ptr(), K2, self.fwd_end_ext[0].data_ptr(), K2, self.err[0:1],
+            ops.seam_check_fix(1, K2, est[0].data_ptr(), K2, self.fwd_end_ext[0].data_ptr(), K2, err[0:1],
                                self.seam_tol, fix, counter)
             lo = 1
         if lo < S:          # true message in front of chain c >= 1: row t_begin(c) - 1 of the filtered posterior
             row = self.alpha[self.core.start + lo * self.chunk_len - 1]
             ops.seam_check_fix(S - lo, K2, est[lo].data_ptr(), K2, row.data_ptr(), self.chunk_len * K2,
-                               self.err[lo:S], self.seam_tol, fix, counter)
+                               err[lo:S], self.seam_tol, fix, counter)
 
-    def _check_bwd(self, hi, fix, counter):
+    def _check_bwd(self, hi, fix, counter, err=None):
         """Backward seams 0..hi-1 (seam c sits behind chain c; its truth is the next chain's first message)."""
         S, K2 = self.S, 2 * self.K
+        err = self.err if err is None else err
         if hi > 0:
             ops.seam_check_fix(hi, K2, self.beta_halo.data_ptr(), K2, self.beta_end[1].data_ptr(), K2,
-                               self.err[S:S + hi], self.seam_tol, fix, counter)
+                               err[S:S + hi], self.seam_tol, fix, counter)
 
     def _truth_fwd(self, ids, compact):
         """true forward messages in front of the chains `ids` (host repair sweeps)"""
@@ -297,32 +314,50 @@ class EStep:
             self.shard.allreduce_flat_sum_(self.tail)
         self.tail_host.copy_(self.tail, non_blocking=True)
         self.err_host.copy_(self.err, non_blocking=True)
+        self.err1_host.copy_(self.err1, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         t = self.tail_host
         return self.err_host, bool(not (t[T_FAIL_F] == 0)), bool(not (t[T_FAIL_B] == 0))
 
-    def _adapt(self, n_fix):
-        """Warm-up of the pass after next from this pass's record (identical on every rank: the record is global).
-        A device repair costs about one chunk of scan time at low occupancy; a longer warm-up costs every chain:
-        repairs are tolerated while the chunks are short compared with the warm-up they would save."""
+    def _adapt(self, n_fail, failed_f, failed_b):
+        """Plans the warm-ups of the pass after next from this pass's record.  n_fail: seams repaired anywhere
+        (global: the common base must be the same on every rank, neighbours exchange messages at positions derived
+        from it); failed_f / failed_b: this rank's chains whose forward / backward seam failed."""
         cur, nxt = self.halos
         new = nxt
-        if self.adaptive:
-            tolerated = self.chunk_len <= 2 * nxt
-            if n_fix > 0 and not tolerated:
-                self._calm = 0
-                if nxt < self.halo:
-                    new = min(self.halo, 2 * nxt)
-                    self._hold = 8
-            elif n_fix == 0:
-                self._calm += 1
-                if self._calm >= 2 and self._hold == 0 and nxt > self.halo_min:
-                    new = max(self.halo_min, nxt // 2)
-                    self._calm = 0
-            else:
-                self._calm = 0
-            if self._hold:
-                self._hold -= 1
+        if not self.adaptive:
+            self.halos = [nxt, new]
+            return
+        import numpy as np
+        S = self.S
+        mass = n_fail > 0.1 * S * self.shard.world            # e.g. a nearly flat model: nothing forgets quickly
+        if n_fail == 0:
+            self._calm += 1
+        else:
+            self._calm = 0
+        if mass and nxt < self.halo:
+            new = min(self.halo, 2 * nxt)
+        elif self._calm >= 2 and nxt > self.halo_min:
+            new = max(self.halo_min, nxt // 2)
+            self._calm = 0
+        c, n = self.h_cur, 1 - self.h_cur
+        for failed, boost, host, dev in ((failed_f, self.boost_f, self.hf_host, self.hf),
+                                         (failed_b, self.boost_b, self.hb_host, self.hb)):
+            bumped = False
+            if failed.size and not mass:
+                # the chains that failed double the warm-up they had in this pass -- for the next pass too (its
+                # warm-start message was taken for the shorter warm-up: it starts from a message of a nearby bin)
+                want = np.minimum(self.boost_cap, 2 * host[c][failed]).astype(np.int32)
+                boost[failed] = np.maximum(boost[failed], want)
+                bumped = bool((host[n][failed] < boost[failed]).any())
+                host[n][failed] = np.maximum(host[n][failed], boost[failed])
+            if bumped:
+                dev[n].copy_(torch.from_numpy(host[n]))
+            plan2 = np.maximum(np.int32(new), boost).astype(np.int32)       # the pass after next
+            if not np.array_equal(plan2, host[c]):
+                host[c][:] = plan2
+                dev[c].copy_(torch.from_numpy(host[c]))
+        self.h_cur = n
         self.halos = [nxt, new]
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
@@ -350,11 +385,14 @@ class EStep:
         f_in = self.fwarm[cur] if self.warm_valid else getattr(self.op, "stationary", None)
         b_in = self.bwarm[cur][1:] if self.warm_valid else None
         b_out = self.bwarm[nxt][1:]
-        err_f, err_b = self.err[0:S], self.err[S:2 * S]
+        err_f, err_b = self.err1[0:S], self.err1[S:2 * S]           # first check: selects the device repairs
         tol = self.seam_tol
+        hf = (self.hf[self.h_cur], self.hf[1 - self.h_cur]) if self.adaptive else (None, None)
+        hb = (self.hb[self.h_cur], self.hb[1 - self.h_cur]) if self.adaptive else (None, None)
 
         def fwd(mode=0, ids=None):
             sel = dict(sel_err=err_f, sel_tol=tol) if mode == 2 else {}
+            ops.set_chain_halos(self.plan, *hf)
             if compact:
                 ops.forward_compact(self.plan, self.op, self.ll, self.ax,
                                     halo_state=(self.halo_state if mode == 0 else None), fwd_end=self.fwd_end,
@@ -367,6 +405,7 @@ class EStep:
 
         def bwd(mode=0, ids=None):
             sel = dict(sel_err=err_b, sel_tol=tol) if mode == 2 else {}
+            ops.set_chain_halos(self.plan, *hb)
             if compact:
                 ops.backward_compact(self.plan, self.op, self.ll, self.ax, gamma16, beta_halo=self.beta_halo,
                                      beta_end=self.beta_end, mode=mode, chain_ids=ids,
@@ -385,7 +424,7 @@ class EStep:
         # neighbour rank is verified after the exchange (its repair, rare, is the host's)
         fwd()
         if S > 1 and self.device_repair:
-            self._check_fwd(compact, 1, True, self.tail[T_FIX_F:T_FIX_F + 1])
+            self._check_fwd(compact, 1, True, self.tail[T_FIX_F:T_FIX_F + 1], err=self.err1)
             fwd(mode=2)
         self._exchange_fwd(compact, nxt)
         if seams:
@@ -395,7 +434,7 @@ class EStep:
         # ---- backward, same structure
         bwd()
         if S > 1 and self.device_repair:
-            self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1])
+            self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1], err=self.err1)
             bwd(mode=2)
         self._exchange_bwd(nxt)
         if seams:
@@ -403,6 +442,7 @@ class EStep:
         ops.phase("backward")
 
         n_relay_f = n_relay_b = 0
+        host_bad_f, host_bad_b = [], []
         err, any_f, any_b = self._verdict(before_sync)
         n_fix_f, n_fix_b = int(self.tail_host[T_FIX_F]), int(self.tail_host[T_FIX_B])
         repaired = bool(any_f or any_b)
@@ -423,6 +463,8 @@ class EStep:
             bad_b = torch.nonzero(~(eb <= tol)).flatten()
             n_relay_f += int(bad_f.numel())
             n_relay_b += int(bad_b.numel())
+            host_bad_f.append(bad_f)
+            host_bad_b.append(bad_b)
             if bad_f.numel():
                 idl = bad_f.to(device=self.dev)
                 self.halo_state[idl] = self._truth_fwd(idl, compact)          # carry snapshot = new "estimate"
@@ -447,7 +489,13 @@ class EStep:
         if seams:
             self.warm_cur, self.warm_valid = nxt, True
         halo_used = self.halos[0]
-        self._adapt(n_fix_f + n_fix_b + n_relay_f + n_relay_b)
+        if self.adaptive:
+            e1 = self.err1_host
+            fail_f = torch.cat([torch.nonzero(~(e1[1:S] <= tol)).flatten() + 1] + host_bad_f).unique().numpy()
+            fail_b = torch.cat([torch.nonzero(~(e1[S:2 * S - 1] <= tol)).flatten()] + host_bad_b).unique().numpy()
+            self._adapt(n_fix_f + n_fix_b + n_relay_f + n_relay_b, fail_f, fail_b)
+        else:
+            self._adapt(0, None, None)
 
         c = self.core
         ef, eb = err[self.f_lo:S], err[S:S + self.b_hi]

@@ -352,7 +352,17 @@ def make_plan(T, core_begin, core_end, chunk_len, halo, left_exact, right_exact,
     p.likelihood_scale = float(likelihood_scale)
     p.halo_next = int(halo_next)
     p.sel_tol, p.sel_err = 0.0, None
+    p.halo_arr = p.halo_next_arr = None
     return p
+
+
+def set_chain_halos(plan, cur=None, nxt=None):
+    """Per-chain warm-up lengths (device int32 [n_chain]) of this pass / the next pass, or None for the scalars."""
+    for t in (cur, nxt):
+        if t is not None and (t.dtype != torch.int32 or t.numel() < plan.n_chain or not t.is_contiguous()):
+            raise ValueError("per-chain halos must be contiguous int32 [n_chain]")
+    plan.halo_arr = cur.data_ptr() if cur is not None else None
+    plan.halo_next_arr = nxt.data_ptr() if nxt is not None else None
 
 
 def _select(plan, mode, sel_err, sel_tol):

@@ -50,8 +50,17 @@ def _slot(buf, s):
     return b if b.ndim == 2 else b[s]
 
 
-def _halo_next(plan):
+def _halo_next(plan, j=None):
+    """warm-up length chain j uses in the next pass (per-chain array of the plan, else the scalar)"""
+    if j is not None and plan.halo_next_arr and 0 <= j < plan.n_chain:
+        return int(ctypes.c_int32.from_address(int(plan.halo_next_arr) + 4 * j).value)
     return int(plan.halo_next) if int(plan.halo_next) > 0 else int(plan.halo)
+
+
+def _halo_own(plan, s):
+    if plan.halo_arr:
+        return int(ctypes.c_int32.from_address(int(plan.halo_arr) + 4 * s).value)
+    return int(plan.halo)
 
 
 def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None, warm_in=None,
@@ -72,7 +81,7 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
             elif carry_in is not None:
                 msg = _np(carry_in)
         else:
-            t0 = t_begin - plan.halo
+            t0 = t_begin - _halo_own(plan, s)
             if t0 <= 0 and plan.left_exact:
                 t0 = 0
                 if carry_in is not None:
@@ -98,7 +107,7 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
                 lmr_[t] = np.float32(np.log(c) + scale * mx)
             elif t == t_begin - 1 and halo_state is not None:
                 _np(halo_state)[s] = m.astype(np.float32)
-            if (warm_out is not None and t == t_end - _halo_next(plan) - 1
+            if (warm_out is not None and t == t_end - _halo_next(plan, s + 1) - 1
                     and (s + 1 < plan.n_chain or not plan.right_exact)):
                 _np(warm_out)[s + 1] = m.astype(np.float32)
 
@@ -120,7 +129,7 @@ def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_o
             else:
                 t_hi, init = T - 1, (None if beta_in is None else _np(beta_in))
         else:
-            t_hi = t_end - 1 + plan.halo
+            t_hi = t_end - 1 + _halo_own(plan, s)
             if t_hi >= T - 1 and plan.right_exact:
                 t_hi, init = T - 1, (None if beta_in is None else _np(beta_in))
             else:
@@ -165,7 +174,7 @@ def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_o
                 _np(beta_halo)[s] = be.astype(np.float32)
             if t == t_begin and beta_end is not None:
                 _np(beta_end)[s] = be.astype(np.float32)
-            if warm_out is not None and t == t_begin + _halo_next(plan) - 1 and (s >= 1 or not plan.left_exact):
+            if warm_out is not None and t == t_begin + _halo_next(plan, s - 1) - 1 and (s >= 1 or not plan.left_exact):
                 # slot s-1 of the view; s == 0 writes the slot in front of the view (the caller passes buf[1:])
                 wo = warm_out
                 if s >= 1:

@@ -67,8 +67,10 @@ def _tunings(d, n_pass):
     rng = np.random.default_rng(3)
     base = d["tuning_true"].astype(np.float64)
     out = []
+    freeze = int(os.environ.get("PMG_TEST_FREEZE_AFTER", n_pass))      # passes >= freeze see the converged tuning
     for i in range(n_pass):
-        out.append((base * (1.0 + 0.05 * (n_pass - 1 - i) * rng.standard_normal(base.shape) * 0.2 + 0.0)).clip(1e-3))
+        k = 0 if i >= freeze else (n_pass - 1 - i)
+        out.append((base * (1.0 + 0.05 * k * rng.standard_normal(base.shape) * 0.2 + 0.0)).clip(1e-3))
     return out
 
 
@@ -89,7 +91,8 @@ def _worker(rank, world, port, cfg, q, device_repair=1):
         lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else T_total
         y = torch.from_numpy(d["y"][lo:hi].copy())
         op = ops.MoveOperator(host, M, torch.device("cpu"), P0=P[0])
-        es = EStep(y, op, None, None, 1.0, halo=halo, chunk_len=chunk, shard=TimeShard() if world > 1 else None)
+        es = EStep(y, op, None, None, 1.0, halo=halo, chunk_len=chunk, shard=TimeShard() if world > 1 else None,
+                   adaptive=bool(os.environ.get("PMG_TEST_ADAPTIVE")))
         out = []
         for tun in _tunings(d, n_pass):
             res = es.run(torch.from_numpy(tun.astype(np.float32)), want_gamma=True, want_gamma_lat=True,
@@ -98,7 +101,8 @@ def _worker(rank, world, port, cfg, q, device_repair=1):
                         "relay": (res.n_relay_fwd + res.n_fix_fwd, res.n_relay_bwd + res.n_fix_bwd),
                         "host_relay": (res.n_relay_fwd, res.n_relay_bwd),
                         "repaired": res.repaired, "err": (res.seam_err_fwd, res.seam_err_bwd),
-                        "n_chain": res.plan.n_chain})
+                        "n_chain": res.plan.n_chain, "halo": res.halo,
+                        "boosted": (int((es.boost_f > 0).sum() + (es.boost_b > 0).sum()) if es.adaptive else 0)})
         q.put((rank, out))
     except Exception:  # pragma: no cover
         import traceback
@@ -161,6 +165,27 @@ def test_estep_orchestration_matches_sequential_answer(world, device_repair):
     first = sum(sum(got[r][0]["relay"]) for r in range(world))
     last = sum(sum(got[r][n_pass - 1]["relay"]) for r in range(world))
     assert last <= first
+
+
+def test_adaptive_warm_up_shrinks_and_boosts(monkeypatch):
+    """Adaptive warm-up (EM mode): the common base halves while no seam needs a repair, chains whose seam fails get
+    their own longer warm-up, and the posteriors stay equal to the sequential answer throughout (3 ranks)."""
+    monkeypatch.setenv("PMG_TEST_ADAPTIVE", "1")
+    monkeypatch.setenv("PMG_HALO_MIN", "4")
+    monkeypatch.setenv("PMG_TEST_FREEZE_AFTER", "3")
+    cfg = (1152, 12, 24, 32, 96, 12, 7)     # halo 32, chains of 96 bins, 12 passes; the tuning is converged from pass 3
+    want = _oracle(cfg)
+    got = _run(3, cfg)
+    for i in range(cfg[5]):
+        gamma = np.concatenate([got[r][i]["gamma"] for r in range(3)])
+        assert np.max(np.abs(gamma - want[i]["gamma"])) < 2e-5, i
+        for r in range(3):
+            assert abs(got[r][i]["lm"] - want[i]["lm"]) < 1e-5 * abs(want[i]["lm"])
+            assert got[r][i]["halo"] == got[0][i]["halo"]            # the base is global
+    halos = [got[0][i]["halo"] for i in range(cfg[5])]
+    assert halos[0] == 32 and halos[-1] < 32, halos                 # it shrank ...
+    assert all(a >= b or a * 2 >= b for a, b in zip(halos, halos[1:]))
+    assert sum(got[r][-1]["boosted"] for r in range(3)) > 0, halos  # ... and some chains needed their own boost
 
 
 # ---------------------------------------------------------------------------------------------------------

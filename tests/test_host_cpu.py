@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     # int K,kind,W (+4 pad) ; 4 pointers ; float[4]
     assert ctypes.sizeof(PmgTransition) == 16 + 32 + 16
     # 4 x int64 ; 4 x int ; float likelihood_scale, int halo_next, float sel_tol (+4 pad) ; pointer sel_err
-    assert ctypes.sizeof(PmgScanPlan) == 32 + 16 + 16 + 8
+    assert ctypes.sizeof(PmgScanPlan) == 32 + 16 + 16 + 3 * 8
     assert PmgScanPlan.sel_err.offset == 64 and PmgScanPlan.halo_next.offset == 52
 
 
