@@ -6,6 +6,7 @@ Drop-in surface (same names as the reference package ``poor_man_gplvm``):
 """
 from .core import PoissonGPLVMJump1D, compute_transition_posterior_prob  # noqa: F401
 from .gp_kernel import create_transition_prob_1d, generate_basis  # noqa: F401
+from . import batched, model_selection_helper  # noqa: F401
 
 __all__ = ["PoissonGPLVMJump1D", "compute_transition_posterior_prob", "create_transition_prob_1d",
            "generate_basis"]

@@ -10,6 +10,8 @@ tensors and skip the device->host copies).
 """
 from __future__ import annotations
 
+import contextlib
+import functools
 import os
 import time
 
@@ -111,6 +113,18 @@ def compute_transition_posterior_prob(log_acc):
            'log_transition_latent': log_transition_latent,
            'log_transition_dynamics': log_transition_dynamics}
     return res
+
+
+def _on_device(fn):
+    """Runs a public method with the model's device current: every kernel launches on the current device's current
+    stream, so a model built with ``device='cuda:1'`` must not depend on the caller having selected that device."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device if (self._device is not None or torch.cuda.is_available()) else None
+        guard = torch.cuda.device(dev) if (dev is not None and dev.type == "cuda") else contextlib.nullcontext()
+        with guard:
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 class EMLoop:
@@ -345,6 +359,7 @@ class PoissonGPLVMJump1D:
         return hostio.to_numpy(t, out=out) if isinstance(t, torch.Tensor) else np.asarray(t)
 
     # ------------------------------------------------------------------ reference API
+    @_on_device
     def get_tuning(self, params, hyperparam, tuning_basis):
         """softplus(basis @ params)  (reference core.py:772-774).  NumPy in -> NumPy out."""
         Phi, W = self._dev(tuning_basis), self._dev(params)
@@ -361,6 +376,7 @@ class PoissonGPLVMJump1D:
         self.tuning = np.logaddexp(self.tuning_basis @ params, np.float32(0)).astype(np.float32)
         return self.params, self.tuning
 
+    @_on_device
     def init_latent_posterior(self, T, key, random_scale=0.1):
         """reference core.py:571-583 with jax.random's bit stream: uniform(key, (T, K)) * random_scale, row
         normalised.  Returns (log_posterior, posterior) as NumPy arrays; large draws run on the device."""
@@ -422,6 +438,7 @@ class PoissonGPLVMJump1D:
         es.shard.allreduce_sum_(G)
         return ops.xi_finalize(G, self._dev(logP), logM)
 
+    @_on_device
     def _decode_latent(self, y, tuning, hyperparam, log_latent_transition_kernel_l=None,
                        log_dynamics_transition_kernel=None, ma_neuron=None, ma_latent=None, likelihood_scale=1.,
                        n_time_per_chunk=10000, return_device=False, _want_r=True):
@@ -445,6 +462,7 @@ class PoissonGPLVMJump1D:
             return out
         return tuple(None if o is None else self._host(o) for o in out)
 
+    @_on_device
     def decode_latent(self, y, tuning=None, hyperparam={}, ma_neuron=None, ma_latent=None, likelihood_scale=1.,
                       n_time_per_chunk=10000, t_l=None, return_device=False, time_sharded=False, group=None):
         """reference core.py:454-497 (same keys).  time_sharded=True (under torch.distributed): ``y`` is this
@@ -481,6 +499,7 @@ class PoissonGPLVMJump1D:
                                  "seam_err_bwd": res.seam_err_bwd}
         return decoding_res
 
+    @_on_device
     def decode_latent_naive_bayes(self, y, tuning=None, hyperparam={}, ma_neuron=None, ma_latent=None,
                                   likelihood_scale=1., n_time_per_chunk=10000, dt_l=1., t_l=None,
                                   return_device=False):
@@ -497,6 +516,9 @@ class PoissonGPLVMJump1D:
         dt_dev = self._dev(dt_l).reshape(-1)
         if dt_dev.numel() not in (1, T):
             raise ValueError("dt_l must be a scalar or have one entry per time bin")
+        if not bool((dt_dev > 0).all()):
+            # the reference keeps log(tuning*dt + 1e-20) finite at dt = 0; the GEMM form separates log(dt)
+            raise ValueError("dt_l must be positive (a bin of zero or negative duration has no likelihood)")
         if dt_dev.numel() == T and T > 1 and bool((dt_dev != dt_dev[0]).any()):
             em = ops.EmissionOperands(y_dev, ma_n, dt_l=dt_dev)
             dt = 1.0
@@ -512,6 +534,7 @@ class PoissonGPLVMJump1D:
                 'posterior_latent': _rewrap_tsd(conv(torch.exp(log_post)), t_l),
                 'll_per_pos_l': conv(ll)}
 
+    @_on_device
     def m_step(self, param_curr, y, log_posterior_curr, tuning_basis, hyperparam, opt_state_curr=None,
                m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6):
         """reference core.py:802-827: sufficient statistics + Adam loop.  NumPy/torch in, dict out."""
@@ -529,6 +552,7 @@ class PoissonGPLVMJump1D:
                 'final_loss': float(fin[0].item()), 'final_error': float(fin[1].item()),
                 'loss_history': self._host(lh[:n]), 'error_history': self._host(eh[:n])}
 
+    @_on_device
     def fit_em(self, y, hyperparam={}, key=0,
                n_iter=20, log_posterior_init=None, ma_neuron=None, ma_latent=None,
                n_time_per_chunk=10000, dt=1., likelihood_scale=1.,
@@ -577,7 +601,7 @@ class PoissonGPLVMJump1D:
             posterior_key = (jaxprng.as_key(key), random_scale, t_offset, T_total)
             dev_ = self.device
             log_posterior_init = hostio.LazyHostArray(
-                None, shape=(T, K), producer=lambda: ops.threefry_posterior_init(
+                None, shape=(T, K), device=dev_, producer=lambda: ops.threefry_posterior_init(
                     T, K, posterior_key[0], random_scale, dev_, t_offset, T_total, want_log=True)[1])
             loop_init = None
         else:

@@ -415,6 +415,226 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+// CTA-pair version (cta_group::2).  The single-CTA kernel above is bound by the L2 -> shared-memory feed: per K
+// block it pulls 32 KB of counts and 52 KB of log-rate pieces for 256 x 208 outputs.  Here two CTAs of a cluster
+// (the two SMs of a TPC) share every right-hand tile: a work unit is 512 time bins x BN latent bins, each CTA
+// loads its own 2 x 128 rows of counts and HALF of the log-rate rows (58 KB per CTA and K block instead of 84),
+// and the leader issues MMAs of M = 256 that read both halves; each CTA accumulates and drains its own 128-lane
+// accumulators.  Barriers: both CTAs' loads count on the leader's `full`; the leader's commits arrive on both
+// CTAs' `empty` / `tfull` (multicast); both CTAs' epilogue warps arrive on the leader's `tempty`.
+__global__ void __launch_bounds__(EM_THREADS, 1)
+emission_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
+                    const EmissionTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;
+  const uint32_t bh_bytes = (uint32_t)(BN / 2) * TC_BK * 2;          // this CTA's half of one log-rate piece
+  const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * bh_bytes;
+  uint8_t* stg_base = smem + (size_t)p.stages * stage_bytes;                      // 1024-aligned
+  float* ls_s = reinterpret_cast<float*>(stg_base + (size_t)8 * p.ep_nbuf * EP_BUF_BYTES);   // [Kpad]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ls_s + ((p.Kpad + 3) & ~3));
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + EM_MI);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = leader
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    for (int b = 0; b < EM_MI; ++b) mbar_init(&tempty[b], 256);     // 128 epilogue threads of each CTA
+    fence_barrier_init();
+  }
+  for (int k = threadIdx.x; k < p.Kpad; k += blockDim.x) {
+    float v = 0.f;
+    if (k < p.K) {
+      v = p.lam_sum[k];
+      if (p.ma_latent && p.ma_latent[k] == 0.f) v = __int_as_float(0x7fc00000);
+    }
+    ls_s[k] = v;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmC32); tma_prefetch_desc(&tmC16);
+  }
+  if (warp == 2) { tmem_alloc2(tmem_slot, p.tmem_cols); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();                                    // barriers and TMEM of BOTH CTAs are ready
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_mquads = (p.n_mtiles + 2 * EM_MI - 1) / (2 * EM_MI);          // 512-row groups
+  const int n_units = n_mquads * p.n_ntiles;
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // row tile of accumulator mi of this CTA inside the 512-row group: MMA mi covers tiles (2 mi, 2 mi + 1)
+  auto row_tile = [&](int mq, int mi) { return mq * (2 * EM_MI) + 2 * mi + (int)rank; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int unit = cluster; unit < n_units; unit += n_clusters) {
+        const int mq = unit / p.n_ntiles, nt = unit % p.n_ntiles;
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);     // both CTAs' bytes
+#pragma unroll
+          for (int mi = 0; mi < EM_MI; ++mi)      // rows past T are zero-filled by the TMA unit
+            tma_load_2d_pair(sA + mi * TC_A_BYTES, &tmA, &full[stage], kb * TC_BK, row_tile(mq, mi) * TC_BM);
+#pragma unroll
+          for (int pc = 0; pc < EM_PB; ++pc)
+            tma_load_2d_pair(sA + EM_MI * TC_A_BYTES + pc * bh_bytes, &tmBh, &full[stage], kb * TC_BK,
+                             pc * p.Kpad + nt * BN + (int)rank * (BN / 2));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      auto issue = [&](int st, int mi, bool first) {
+        const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(mi * BN);
+#pragma unroll
+        for (int pc = 0; pc < EM_PB; ++pc) {
+          const uint32_t sB = sA + EM_MI * TC_A_BYTES + pc * bh_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sA + mi * TC_A_BYTES + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(sB + k * 32, 16, 1024);
+            mma_f16_ss2(d_tmem, ad, bd, p.idesc, (first && pc == 0 && k == 0) ? 0u : 1u);
+          }
+        }
+      };
+      for (int unit = cluster; unit < n_units; unit += n_clusters, ++it) {
+        const uint32_t drained = (uint32_t)(it & 1) ^ 1;      // parity of "the previous unit's epilogues are done"
+        int kb = 0;
+        if (p.n_kblocks >= 2 && p.stages >= 2) {
+          const int s0 = stage; const uint32_t ph0 = phase;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          const int s1 = stage; const uint32_t ph1 = phase;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          mbar_wait(&full[s0], ph0);
+          mbar_wait(&tempty[0], drained);
+          tc_fence_after();
+          issue(s0, 0, true);
+          mbar_wait(&full[s1], ph1);
+          tc_fence_after();
+          issue(s1, 0, false);
+          mbar_wait(&tempty[1], drained);
+          tc_fence_after();
+          issue(s0, 1, true);
+          mma_commit2(&empty[s0], 3);
+          issue(s1, 1, false);
+          mma_commit2(&empty[s1], 3);
+          kb = 2;
+        }
+        for (; kb < p.n_kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int mi = 0; mi < EM_MI; ++mi) {
+            if (kb == 0) {
+              mbar_wait(&tempty[mi], drained);
+              tc_fence_after();
+            }
+            issue(stage, mi, kb == 0);
+          }
+          mma_commit2(&empty[stage], 3);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit2(tfull, 3);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int mi = (warp - 4) >> 2;              // accumulator (row tile) this warp set drains
+    const uint32_t stg = smem_u32(stg_base + (size_t)(warp - 4) * p.ep_nbuf * EP_BUF_BYTES);
+    const uint32_t ls_addr = smem_u32(ls_s);
+    const uint32_t stg_row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
+    const uint32_t stg_row64 = (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
+    const int nch = (BN + 31) / 32;
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mi * BN);
+    const bool masked = p.ma_latent != nullptr;
+    int it = 0, buf = 0;
+    for (int unit = cluster; unit < n_units; unit += n_clusters, ++it) {
+      const int mq = unit / p.n_ntiles, nt = unit % p.n_ntiles;
+      const int64_t t0 = (int64_t)row_tile(mq, mi) * TC_BM + q * 32;     // first row of this warp
+      const float lg = (t0 + lane) < p.T ? __ldg(p.lgam + t0 + lane) : 0.f;
+      const bool rows_ok = t0 < p.T;
+      mbar_wait(tfull, (uint32_t)(it & 1));
+      tc_fence_after();
+
+      auto issue = [&](int c, uint32_t (&r)[32]) {
+        const int c0 = c * 32;
+        if (c0 + 32 <= BN) tmem_ld_x32(tbase + (uint32_t)c0, r); else tmem_ld_x16_of32(tbase + (uint32_t)c0, r);
+      };
+      auto process = [&](int c, uint32_t (&r)[32]) {
+        const int c0 = c * 32;
+        if (c == nch - 1) {                      // the last chunk of this accumulator has left TMEM
+          tc_fence_before();
+          if (rank == 0) mbar_arrive(&tempty[mi]); else mbar_arrive_cluster(&tempty[mi], 0);
+        }
+        const bool wide = c0 + 32 <= BN;
+        if (lane == 0) {
+          if (p.ep_nbuf == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+        }
+        __syncwarp();
+        const uint32_t sb = stg + (uint32_t)buf * EP_BUF_BYTES;
+        const uint32_t lsp = ls_addr + (uint32_t)(nt * BN + c0) * 4u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!wide && j >= 4) break;
+          const float4 l4 = lds_f4(lsp + 16u * j);
+          float4 v;
+          v.x = __uint_as_float(r[4 * j + 0]) - l4.x - lg;
+          v.y = __uint_as_float(r[4 * j + 1]) - l4.y - lg;
+          v.z = __uint_as_float(r[4 * j + 2]) - l4.z - lg;
+          v.w = __uint_as_float(r[4 * j + 3]) - l4.w - lg;
+          if (masked) {
+            if (l4.x != l4.x) v.x = kVeryNegLL;
+            if (l4.y != l4.y) v.y = kVeryNegLL;
+            if (l4.z != l4.z) v.z = kVeryNegLL;
+            if (l4.w != l4.w) v.w = kVeryNegLL;
+          }
+          const uint32_t off = wide ? stg_row128 + (((uint32_t)j ^ sw128) << 4)
+                                    : stg_row64 + (((uint32_t)j ^ sw64) << 4);
+          sts_f4(sb + off, v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int col0 = nt * BN + c0;
+          if (rows_ok && col0 < p.K) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(wide ? &tmC32 : &tmC16)), "r"(sb), "r"(col0), "r"((int)t0)
+                         : "memory");
+          }
+          bulk_commit();
+        }
+        if (++buf == p.ep_nbuf) buf = 0;
+      };
+
+      uint32_t ra[32], rb[32];
+      issue(0, ra);
+      for (int c = 0; c < nch; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nch) issue(c + 1, rb);
+        process(c, ra);
+        if (c + 1 < nch) {
+          tmem_ld_wait();
+          if (c + 2 < nch) issue(c + 2, ra);
+          process(c + 1, rb);
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();          // shared memory must outlive the last stores' reads
+  }
+  tc_fence_before();
+  cluster_sync_all();                            // the peer may still read this CTA's shared memory / arrive here
+  if (warp == 2) { tc_fence_after(); tmem_dealloc2(tmem_base, p.tmem_cols); }
+}
+
 // previous structure (one 128-row tile per unit, double-buffered accumulator), kept selectable for experiments
 __global__ void __launch_bounds__(TC_THREADS, 1)
 emission_tc_kernel_v1(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -648,6 +868,54 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
 
   // 256-row work units + TMA-store epilogue: needs 16-byte aligned rows of ll
   bool paired = kver_env != 1 && (ldll & 3) == 0 && ((uintptr_t)ll & 15) == 0;
+  // CTA pairs (cta_group::2): 512-row units, every log-rate tile shared by the two SMs of a TPC
+  static const int pair_env = std::getenv("PMG_EM_PAIR") ? std::atoi(std::getenv("PMG_EM_PAIR")) : 0;
+  if (paired && pair_env && (BN % 16) == 0 && T >= 4 * TC_BM) {
+    const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * (BN / 2) * TC_BK * 2;
+    const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (size_t)((Kpad + 3) & ~3) * sizeof(float);
+    int nbuf = 2, stages = 0;
+    for (; nbuf >= 1; --nbuf) {
+      const size_t stg_bytes = (size_t)8 * nbuf * EP_BUF_BYTES;
+      stages = fixed + stg_bytes < smem_max ? (int)((smem_max - fixed - stg_bytes) / stage_bytes) : 0;
+      if (stages >= 3) break;
+    }
+    if (nbuf < 1) { nbuf = 1; }
+    if (stages >= 2) {
+      if (stages > 6) stages = 6;
+      EmissionTcParams p2 = p;
+      p2.stages = stages;
+      p2.ep_nbuf = nbuf;
+      p2.idesc = make_idesc_f16(2 * TC_BM, BN, 0, 0, 0);
+      CUtensorMap tmBh, tmC32, tmC16;
+      rc = make_tmap_f16(&tmBh, loglam16, (uint64_t)EM_PB * Kpad, (uint64_t)ld16, (uint64_t)ld16, (uint32_t)(BN / 2));
+      if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+      rc = make_tmap_f32(&tmC32, ll, (uint64_t)T, (uint64_t)K, (uint64_t)ldll, 32, 32);
+      if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+      rc = make_tmap_f32(&tmC16, ll, (uint64_t)T, (uint64_t)K, (uint64_t)ldll, 32, 16);
+      if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+      const size_t smem = (size_t)stages * stage_bytes + (size_t)8 * nbuf * EP_BUF_BYTES + fixed;
+      PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PMG_CUDA_CHECK(cudaFuncSetAttribute(emission_tc2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.blockDim = dim3(EM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cfg.gridDim = dim3((unsigned)(sms & ~1));
+      int max_clusters = 0;
+      cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, emission_tc2_kernel, &cfg);
+      const int n_units2 = ((p.n_mtiles + 2 * EM_MI - 1) / (2 * EM_MI)) * p.n_ntiles;
+      if (oe == cudaSuccess && max_clusters >= 1) {
+        int n_cl = max_clusters < n_units2 ? max_clusters : n_units2;
+        if (n_cl > sms / 2) n_cl = sms / 2;
+        cfg.gridDim = dim3((unsigned)(2 * n_cl));
+        PMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, emission_tc2_kernel, tmA, tmBh, tmC32, tmC16, p2));
+        return PMG_OK;
+      }
+      (void)cudaGetLastError();          // no co-resident pair on this device/configuration: single-CTA kernel below
+    }
+  }
   if (paired) {
     const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * BN * TC_BK * 2;
     const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (size_t)((Kpad + 3) & ~3) * sizeof(float);

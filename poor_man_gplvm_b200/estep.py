@@ -361,17 +361,21 @@ class EStep:
         self.halos = [nxt, new]
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
-            before_sync=None):
+            before_sync=None, forward_only=False):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
         the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes, the
         device repairs and the seam checks are enqueued, before the launching thread waits for the verdict (work
         enqueued there keeps the GPU busy during the synchronisation; on time-sharded runs it must all-reduce
         ``self.tail`` with its own data; ``res.repaired`` tells whether chains were re-run by the HOST after it,
-        i.e. whether what it read from this E-step's outputs was final)."""
+        i.e. whether what it read from this E-step's outputs was final).
+        forward_only: emission + filter only (log marginal, one-step predictive marginals): what the batched callers
+        of the reference (model selection, shuffle tests) read from decode_latent."""
         S, K = self.S, self.K
+        if forward_only:
+            want_gamma = want_gamma_lat = want_dyn = want_r = False
         f32 = dict(dtype=torch.float32, device=self.dev)
         # EM fast path: only the fp16 posterior pieces and sum_t gamma are wanted -> compact kernels
-        compact = (self.compact_ok and gamma16 is not None
+        compact = (self.compact_ok and (gamma16 is not None or forward_only)
                    and not (want_gamma or want_gamma_lat or want_dyn or want_r))
         self.plan.halo, self.plan.halo_next = int(self.halos[0]), int(self.halos[1])
         self.emission(tuning)
@@ -432,14 +436,15 @@ class EStep:
         self._lml_to_tail(lmr)
         ops.phase("forward")
         # ---- backward, same structure
-        bwd()
-        if S > 1 and self.device_repair:
-            self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1], err=self.err1)
-            bwd(mode=2)
-        self._exchange_bwd(nxt)
-        if seams:
-            self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
-        ops.phase("backward")
+        if not forward_only:
+            bwd()
+            if S > 1 and self.device_repair:
+                self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1], err=self.err1)
+                bwd(mode=2)
+            self._exchange_bwd(nxt)
+            if seams:
+                self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
+            ops.phase("backward")
 
         n_relay_f = n_relay_b = 0
         host_bad_f, host_bad_b = [], []
@@ -474,19 +479,21 @@ class EStep:
                 idb = bad_b.to(device=self.dev)
                 self.beta_halo[idb] = self.beta_end[idb + 1]
             both = torch.unique(torch.cat([bad_f, bad_b]))
-            if both.numel():
+            if both.numel() and not forward_only:
                 bwd(mode=1, ids=both.to(device=self.dev, dtype=torch.int32))
-            self._exchange_bwd(nxt)
+            if not forward_only:
+                self._exchange_bwd(nxt)
             self.tail.zero_()
             self._check_fwd(compact, self.f_lo, False, self.tail[T_FAIL_F:T_FAIL_F + 1])
-            self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
+            if not forward_only:
+                self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
             self._lml_to_tail(lmr)
             err, any_f, any_b = self._verdict()
         if any_f or any_b:
             raise RuntimeError("E-step: seams still above seam_tol=%g after %d repair sweeps (worst forward %.3g, "
                                "backward %.3g)" % (tol, self.max_sweeps, float(err[self.f_lo:S].max()) if S > self.f_lo
                                                    else 0.0, float(err[S:S + self.b_hi].max()) if self.b_hi else 0.0))
-        if seams:
+        if seams and not forward_only:           # (a forward-only pass leaves no backward warm starts behind)
             self.warm_cur, self.warm_valid = nxt, True
         halo_used = self.halos[0]
         if self.adaptive:
@@ -510,7 +517,7 @@ class EStep:
         res.r = r[c] if r is not None else None
         # local sums; the caller all-reduces them together with the spike-weighted statistics
         # (the compact path leaves sum_t gamma to the statistics GEMM: ones column of the fp16 counts)
-        res.tw = None if compact else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
+        res.tw = None if (compact or forward_only) else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
         # global (summed over ranks) log marginal: a host scalar, it came with the verdict
         res.log_marginal = self.tail_host[T_LML].clone()
         res.n_relay_fwd, res.n_relay_bwd = n_relay_f, n_relay_b

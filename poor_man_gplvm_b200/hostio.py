@@ -199,23 +199,42 @@ class LazyHostArray(np.lib.mixins.NDArrayOperatorsMixin):
     copy, so derived quantities cost no device memory until someone asks for them.
     """
 
-    def __init__(self, tensor, transform=None, shape=None, producer=None):
+    def __init__(self, tensor, transform=None, shape=None, producer=None, device=None):
         """tensor: device tensor, or None with `producer` (a callable returning the device tensor, run on
-        first use) and `shape`."""
+        first use), `shape` and the `device` the producer launches on."""
         self._tensor = tensor
         self._producer = producer
         self._shape = tuple(shape) if shape is not None else None
         self._f = transform
         self._host = None
+        self._device = tensor.device if tensor is not None else device
+
+    def _guard(self):
+        """kernels behind the producer / transform launch on the tensor's device, whatever device is current"""
+        import contextlib
+        d = self._device
+        if d is not None and torch.device(d).type == "cuda":
+            return torch.cuda.device(d)
+        return contextlib.nullcontext()
 
     @property
     def _t(self):
         if self._tensor is None:
-            self._tensor = self._producer()
+            with self._guard():
+                self._tensor = self._producer()
         return self._tensor
 
     def device_tensor(self):
-        return self._t if self._f is None else self._f(self._t)
+        if self._f is None:
+            return self._t
+        t = self._t
+        with self._guard():
+            return self._f(t)
+
+    def __reduce__(self):
+        """Pickles as the materialised NumPy array (the reference's jax arrays pickle to host data too); a live
+        device tensor or a local producer would tie the pickle to this process and its GPU."""
+        return (np.asarray, (np.array(self.numpy()),))
 
     def numpy(self):
         if self._host is None:

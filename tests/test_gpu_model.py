@@ -193,3 +193,36 @@ def test_fit_em_default_key_draws_reference_posterior_on_device():
     assert np.allclose(np.asarray(r1["log_posterior_init"]), lp0, rtol=0, atol=2e-6)
     assert np.allclose(r1["log_marginal_l"], r2["log_marginal_l"], rtol=2e-6)
     assert np.max(np.abs(r1["posterior_latent_marg"] - r2["posterior_latent_marg"])) < 2e-5
+
+
+def test_results_pickle_and_reject_bad_dt():
+    """em_res / decoding_res round-trip through pickle as host arrays; per-bin dt must be positive."""
+    d, model, oracle, lp0 = _pair(12, 32, 200, 6.0, seed=21)
+    em = model.fit_em(d["y"], n_iter=2, m_step_maxiter=10, m_step_tol=-1)      # default key: lazy initial posterior
+    dec = model.decode_latent(d["y"])
+    em2, dec2 = pickle.loads(pickle.dumps(em)), pickle.loads(pickle.dumps(dec))
+    assert set(em2) == EM_KEYS and set(dec2) == DECODE_KEYS
+    assert np.array_equal(np.asarray(em["log_posterior_final"]), em2["log_posterior_final"])
+    assert np.array_equal(np.asarray(em["log_posterior_init"]), em2["log_posterior_init"])
+    assert np.array_equal(np.asarray(dec["p_joint_full"]), dec2["p_joint_full"])
+    dt = np.ones(200, np.float32); dt[7] = 0.0
+    with pytest.raises(ValueError):
+        model.decode_latent_naive_bayes(d["y"], dt_l=dt)
+
+
+def test_model_on_a_device_that_is_not_current():
+    """device='cuda:1' while cuda:0 is current: every launch must land on the model's device (needs 2 GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import poor_man_gplvm_b200 as pmg
+    N, K, T = 20, 64, 500
+    d = make_dataset(T, N, K, seed=22)
+    torch.cuda.set_device(0)
+    m0 = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=8.0, device="cuda:0")
+    m1 = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=8.0, device="cuda:1")
+    kw = dict(n_iter=3, key=3, m_step_maxiter=15, m_step_tol=-1)
+    r0, r1 = m0.fit_em(d["y"], **kw), m1.fit_em(d["y"], **kw)
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(r0["tuning"], r1["tuning"]) and np.array_equal(r0["posterior"], r1["posterior"])
+    assert np.array_equal(np.asarray(m0.decode_latent(d["y"])["posterior_all"]),
+                          np.asarray(m1.decode_latent(d["y"])["posterior_all"]))

@@ -208,3 +208,34 @@ def test_host_buffers_prefault_and_hand_out_arrays():
     x[:] = 7
     hostio._touch(x[50:2 * 4096 + 77])
     assert int(x.min()) == 7 or int(x[50:2 * 4096 + 77].max()) in (0, 7)
+
+
+def test_lazy_host_array_pickles_as_numpy():
+    """em_res / decoding_res hold LazyHostArray objects (device tensors copied on first use); they must pickle to
+    plain host data like the reference's jax arrays, including the ones built around a local producer."""
+    import pickle
+    import torch
+    from poor_man_gplvm_b200 import hostio
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4) + 1
+    res = {"a": hostio.LazyHostArray(t, torch.log),
+           "b": hostio.LazyHostArray(None, shape=(3, 4), producer=lambda: t * 2)}
+    back = pickle.loads(pickle.dumps(res))
+    assert isinstance(back["a"], np.ndarray) and isinstance(back["b"], np.ndarray)
+    assert np.allclose(back["a"], np.log(t.numpy())) and np.array_equal(back["b"], (t * 2).numpy())
+
+
+def test_circular_shuffle_and_latent_masks_on_host():
+    """test.py:10-24 / model_selection_helper.py:249-254 helpers that need no GPU."""
+    from poor_man_gplvm_b200 import test as shuf, model_selection_helper as msh
+    y = np.arange(20, dtype=np.float32).reshape(5, 4)
+    shifts = np.array([[0, 1, 2, 5], [3, 3, 3, 3]])
+    out = list(shuf.circular_shuffle_data(y, n_shuffle=2, shifts=shifts))
+    for i in range(2):
+        for j in range(4):
+            assert np.array_equal(out[i][:, j], np.roll(y[:, j], shifts[i, j]))
+    masks = msh.draw_latent_masks(40, 0.2, 6, key=4)
+    assert masks.shape == (6, 40) and set(np.unique(masks)) == {0.0, 1.0} and np.all(masks.sum(axis=1) == 8)
+    assert np.array_equal(masks, msh.draw_latent_masks(40, 0.2, 6, key=4))
+    e = shuf.compute_entropy(np.log(np.full((3, 2, 4), 1 / 8)))
+    assert np.allclose(e, np.log(8))
+    assert shuf.compute_entropy(np.array([[0.0, -np.inf]]), axis=-1)[0] == 0.0
