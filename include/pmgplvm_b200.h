@@ -66,6 +66,13 @@ int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int64_t ldy, c
                          const float* lam_sum, const float* lgam, const float* ma_latent,
                          float* ll, int64_t ldll, pmg_stream_t stream);
 
+/* Gaussian observation model (decoder.py:50-57; GaussianGPLVMJump1D / GaussianGPLVM1D):
+ * ll[t,k] = sum_n m * (-(y[t,n] - mu[k,n])^2 / (2 s^2) - log(2 pi s^2) / 2), -1e20 where ma_latent[k] == 0.
+ * ma_neuron: NULL, [N] (ld_mask = 0) or [T, ld_mask]. */
+int pmg_emission_gaussian(int64_t T, int N, int K, const float* y, int64_t ldy, const float* mu,
+                          const float* ma_neuron, int64_t ld_mask, float noise_std, const float* ma_latent,
+                          float* ll, int64_t ldll, pmg_stream_t stream);
+
 /* Tensor-core path (tcgen05 kind::f16, TMA-fed, fp32 accumulation in TMEM).
  * y16: fp16 copy of the counts, [T, ld16] with ld16 % 8 == 0 and zero padding; *inexact_count (device)
  *      = number of entries that fp16 does not represent exactly (caller must use the fp32 path if > 0).

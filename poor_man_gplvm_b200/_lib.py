@@ -44,6 +44,8 @@ SIGNATURES = {
                                            C.c_int64, c_f32p, c_stream]),
     "pmg_emission_poisson": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p,
                                        c_f32p, c_f32p, C.c_int64, c_stream]),
+    "pmg_emission_gaussian": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64,
+                                        C.c_float, c_f32p, c_f32p, C.c_int64, c_stream]),
     "pmg_counts_prepare": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_void_p, C.c_int64, C.c_int,
                                      c_i32p, c_f32p, c_f32p, c_stream]),
     "pmg_counts_to_f16": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, C.c_void_p, C.c_int64, c_i32p, c_stream]),

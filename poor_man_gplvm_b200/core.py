@@ -133,9 +133,12 @@ class EMLoop:
     ``fit_em``: statistics -> Adam M-step -> tuning -> E-step."""
 
     def __init__(self, model, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, log_posterior_init, prior_std,
-                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None, shard=None, posterior_key=None):
+                 step_size=0.01, maxiter=1000, tol=1e-6, halo=None, chunk_len=None, shard=None, posterior_key=None,
+                 emission_factory=None, carry_in=None, mstep_fn=None):
         """log_posterior_init: [T,K] array, or None with posterior_key = (key, random_scale, t_offset, T_total):
-        the reference's random initial posterior (core.py:571-583) drawn on the device."""
+        the reference's random initial posterior (core.py:571-583) drawn on the device.
+        emission_factory / carry_in: see EStep (other observation models, latent-only families);
+        mstep_fn(Phi, yw, tw, W) -> tuning [K,N] replaces the Adam M-step (updates W in place; Gaussian families)."""
         self.y = y_dev
         self.Phi = model._dev(tuning_basis)
         self.W = model._dev(model.params).clone()
@@ -147,8 +150,9 @@ class EMLoop:
         K_, N1 = op.K, model.n_neuron + 1
         self.pack = torch.zeros(K_ * N1 + estep.TAIL, dtype=torch.float32, device=self.W.device)
         self.stats = self.pack[:K_ * N1].view(K_, N1)
+        self.mstep_fn = mstep_fn
         self.es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, halo=halo, chunk_len=chunk_len, shard=shard,
-                        em_mode=True, tail=self.pack[K_ * N1:])
+                        em_mode=True, tail=self.pack[K_ * N1:], emission_factory=emission_factory, carry_in=carry_in)
         self.shard = self.es.shard
         self.broadcast_mstep = os.environ.get("PMG_MSTEP_BROADCAST", "0") != "0"
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
@@ -216,6 +220,12 @@ class EMLoop:
         # time-sharded ranks: one all-reduce (fp32 on the wire, in place, no packing copies)
         self.shard.allreduce_flat_sum_(self.pack if with_record else self.pack[:self.stats.numel()])
         ops.phase("stats")
+        if self.mstep_fn is not None:
+            self._tuning_i ^= 1
+            tun = self._tuning[self._tuning_i]
+            tun.copy_(self.mstep_fn(self.Phi, self.stats[:, :N], self.stats[:, N], self.W))
+            ops.phase("mstep")
+            return (None, None, None, None, tun)
         m_res = ops.mstep_adam(self.Phi, self.stats[:, :N], self.stats[:, N], self.W, self.state, self.prior_std,
                                self.step_size, self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
         if self.shard.active and self.broadcast_mstep:
@@ -358,6 +368,15 @@ class PoissonGPLVMJump1D:
         """device tensor -> NumPy (pinned, pipelined copy for the T-sized arrays)"""
         return hostio.to_numpy(t, out=out) if isinstance(t, torch.Tensor) else np.asarray(t)
 
+    # ------------------------------------------------------------------ hooks of the other families (families.py)
+    def _emission_factory(self, hyperparam):
+        """callable(y_ext, ma_neuron) -> emission operand, or None for the Poisson model of this class"""
+        return None
+
+    def _mstep_fn(self, hyperparam):
+        """callable(Phi, yw, tw, W) -> tuning replacing the Adam M-step, or None"""
+        return None
+
     # ------------------------------------------------------------------ reference API
     @_on_device
     def get_tuning(self, params, hyperparam, tuning_basis):
@@ -451,7 +470,7 @@ class PoissonGPLVMJump1D:
         y_dev = self._dev(y)
         P, logP, M, logM, op = self._transition_pack(hyperparam)
         ma_n, ma_l = self._masks(ma_neuron, ma_latent, y_dev.shape[0])
-        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale)
+        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, emission_factory=self._emission_factory(hyperparam))
         res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=False, want_dyn=False, want_r=_want_r)
         log_acc = None
         if _want_r and y_dev.shape[0] > 1:
@@ -477,7 +496,8 @@ class PoissonGPLVMJump1D:
         T, K = y_dev.shape[0], self.n_latent_bin
         P, logP, M, logM, op = self._transition_pack(hyperparam)
         ma_n, ma_l = self._masks(ma_neuron, ma_latent, T)
-        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, shard=TimeShard(group) if time_sharded else None)
+        es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, shard=TimeShard(group) if time_sharded else None,
+                   emission_factory=self._emission_factory(hyperparam))
         res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=True, want_dyn=True,
                      want_r=(T > 1 or es.shard.active))
         conv = (lambda t: t) if return_device else self._host
@@ -519,11 +539,14 @@ class PoissonGPLVMJump1D:
         if not bool((dt_dev > 0).all()):
             # the reference keeps log(tuning*dt + 1e-20) finite at dt = 0; the GEMM form separates log(dt)
             raise ValueError("dt_l must be positive (a bin of zero or negative duration has no likelihood)")
+        factory = self._emission_factory(hyperparam)
         if dt_dev.numel() == T and T > 1 and bool((dt_dev != dt_dev[0]).any()):
+            if factory is not None:
+                raise ValueError("per-bin dt_l is implemented for the Poisson model only")
             em = ops.EmissionOperands(y_dev, ma_n, dt_l=dt_dev)
             dt = 1.0
         else:
-            em = ops.EmissionOperands(y_dev, ma_n)
+            em = factory(y_dev, ma_n) if factory is not None else ops.EmissionOperands(y_dev, ma_n)
             dt = float(dt_dev[0].item()) if dt_dev.numel() else 1.0
         ll = em.loglik(self._dev(tuning), ma_l, dt)
         log_post, lml = ops.naive_bayes_normalize(ll)
@@ -606,8 +629,10 @@ class PoissonGPLVMJump1D:
             loop_init = None
         else:
             loop_init = log_posterior_init
+        mstep_fn = self._mstep_fn(hyperparam_)
         loop = EMLoop(self, y_dev, op, ma_n, ma_l, likelihood_scale, tuning_basis, loop_init, prior_std,
-                      m_step_step_size, m_step_maxiter, m_step_tol, shard=shard, posterior_key=posterior_key)
+                      m_step_step_size, m_step_maxiter, m_step_tol, shard=shard, posterior_key=posterior_key,
+                      emission_factory=self._emission_factory(hyperparam_), mstep_fn=mstep_fn)
         self.opt_state_init_fun = ops.AdamState
         W, state, es = loop.W, loop.state, loop.es
         tm.mark("setup")
@@ -649,6 +674,8 @@ class PoissonGPLVMJump1D:
         tm.mark("em_loop")
         lml_host = torch.stack(lml_dev).cpu().numpy().astype(np.float32) if lml_dev else np.zeros(0, np.float32)
         saved['log_marginal_saved'] = [np.float32(v.item()) for v in saved['log_marginal_saved']]
+        if mstep_fn is not None:
+            m_hist = []                            # analytic M-step: no optimiser histories (reference core.py:885-892)
         n_its = torch.cat([h[2] for h in m_hist]).cpu().numpy() if m_hist else np.zeros(0, np.int32)
         m_step_res_l = {'n_iter': [int(n) for n in n_its],
                         'final_loss': [float(h[3][0].item()) for h in m_hist],

@@ -180,6 +180,85 @@ __global__ void __launch_bounds__(256) emission_simt_kernel(int64_t T, int N, in
   }
 }
 
+// ---- Gaussian observation model (reference decoder.py:50-57): ll[t,k] = sum_n m (-(y - mu_kn)^2 / (2 s^2)
+// - log(2 pi s^2) / 2).  Same tiling as the fp32 emission GEMM with the squared difference as the inner operation
+// (the expanded GEMM form y mu - mu^2/2 cancels catastrophically in fp32 for real-valued observations).
+// ma: NULL, a vector [N] (ld_mask = 0) or a [T, ld_mask] mask. ----
+__global__ void __launch_bounds__(256) emission_gaussian_kernel(int64_t T, int N, int K,
+                                                                const float* __restrict__ y, int64_t ldy,
+                                                                const float* __restrict__ mu,
+                                                                const float* __restrict__ ma, int64_t ld_mask,
+                                                                float inv_2var, float half_log_2pivar,
+                                                                const float* __restrict__ ma_latent,
+                                                                float* __restrict__ ll, int64_t ldll) {
+  __shared__ float As[EM_BK][EM_BM + 4];
+  __shared__ float Ws[EM_BK][EM_BM + 4];
+  __shared__ float Bs[EM_BK][EM_BN + 4];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int64_t t0 = (int64_t)blockIdx.x * EM_BM;
+  const int k0 = blockIdx.y * EM_BN;
+  float acc[8][4], wsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    wsum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  for (int n0 = 0; n0 < N; n0 += EM_BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, cc = idx & 15;
+      const int64_t t = t0 + r;
+      const int n = n0 + cc;
+      const bool ok = t < T && n < N;
+      As[cc][r] = ok ? y[(size_t)t * ldy + n] : 0.f;
+      float w = 0.f;
+      if (ok) w = !ma ? 1.f : (ld_mask ? ma[(size_t)t * ld_mask + n] : ma[n]);
+      Ws[cc][r] = w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, cc = idx & 15;
+      const int k = k0 + r;
+      const int n = n0 + cc;
+      Bs[cc][r] = (k < K && n < N) ? mu[(size_t)k * N + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < EM_BK; ++kk) {
+      float a[8], w[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] = As[kk][ty * 8 + i]; w[i] = Ws[kk][ty * 8 + i]; wsum[i] += w[i]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = a[i] - b[j];
+          acc[i][j] = fmaf(w[i] * d, d, acc[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t t = t0 + ty * 8 + i;
+    if (t >= T) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= K) continue;
+      float v = -inv_2var * acc[i][j] - half_log_2pivar * wsum[i];
+      if (ma_latent && ma_latent[k] == 0.f) v = kVeryNegLL;
+      ll[(size_t)t * ldll + k] = v;
+    }
+  }
+}
+
 // one warp per time bin: lml = logsumexp_k ll, log_post = ll - lml
 __global__ void nb_normalize_kernel(int64_t T, int K, const float* __restrict__ ll, int64_t ldll,
                                     float* __restrict__ log_post, int64_t ldp, float* __restrict__ lml_t) {
@@ -206,6 +285,19 @@ extern "C" int pmg_emission_prepare(int K, int N, const float* tuning, const flo
                                     float* loglam, float* lam_sum, pmg_stream_t stream) {
   if (K <= 0 || N <= 0 || !tuning || !loglam || !lam_sum) return PMG_ERR_BAD_ARG;
   pmg::emission_prepare_kernel<<<K, 128, 0, (cudaStream_t)stream>>>(K, N, tuning, ma_neuron, dt, loglam, lam_sum);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_emission_gaussian(int64_t T, int N, int K, const float* y, int64_t ldy, const float* mu,
+                                     const float* ma_neuron, int64_t ld_mask, float noise_std, const float* ma_latent,
+                                     float* ll, int64_t ldll, pmg_stream_t stream) {
+  if (T <= 0 || N <= 0 || K <= 0 || !y || !mu || !ll || ldy < N || ldll < K || !(noise_std > 0.f)) return PMG_ERR_BAD_ARG;
+  if (ld_mask != 0 && ld_mask < N) return PMG_ERR_BAD_ARG;
+  const float var = noise_std * noise_std;
+  dim3 grid((unsigned)pmg::cdiv(T, pmg::EM_BM), (unsigned)pmg::cdiv(K, pmg::EM_BN));
+  pmg::emission_gaussian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      T, N, K, y, ldy, mu, ma_neuron, ld_mask, 0.5f / var, 0.5f * logf(6.283185307179586f * var), ma_latent, ll, ldll);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

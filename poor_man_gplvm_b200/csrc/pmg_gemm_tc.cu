@@ -869,7 +869,7 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   // 256-row work units + TMA-store epilogue: needs 16-byte aligned rows of ll
   bool paired = kver_env != 1 && (ldll & 3) == 0 && ((uintptr_t)ll & 15) == 0;
   // CTA pairs (cta_group::2): 512-row units, every log-rate tile shared by the two SMs of a TPC
-  static const int pair_env = std::getenv("PMG_EM_PAIR") ? std::atoi(std::getenv("PMG_EM_PAIR")) : 0;
+  static const int pair_env = std::getenv("PMG_EM_PAIR") ? std::atoi(std::getenv("PMG_EM_PAIR")) : 1;
   if (paired && pair_env && (BN % 16) == 0 && T >= 4 * TC_BM) {
     const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * (BN / 2) * TC_BK * 2;
     const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (size_t)((Kpad + 3) & ~3) * sizeof(float);

@@ -47,6 +47,7 @@ MIN_CHUNK = int(os.environ.get("PMG_MIN_CHUNK", "64"))
 EM_CHAINS_PER_SM = 12
 
 # record shared with the caller's collective: log marginal, then (repaired on device, still failing) per pass
+_NO_CHAINS = __import__("numpy").zeros(0, dtype="int64")
 TAIL = 5
 T_LML, T_FIX_F, T_FAIL_F, T_FIX_B, T_FAIL_B = range(TAIL)
 
@@ -75,11 +76,15 @@ class EStep:
     """Buffers and launch plan for repeated E-steps over the same spike matrix (this rank's block)."""
 
     def __init__(self, y, op, ma_neuron=None, ma_latent=None, likelihood_scale=1.0, halo=None, seam_tol=None,
-                 chunk_len=None, emission_impl=0, shard=None, em_mode=False, tail=None, adaptive=None):
+                 chunk_len=None, emission_impl=0, shard=None, em_mode=False, tail=None, adaptive=None,
+                 emission_factory=None, carry_in=None):
         """em_mode: the plan is sized for the compact EM kernels (more, shorter chains) when they apply and the
         warm-up length adapts from pass to pass.  tail: optional 5-float device view the E-step writes its record
-        into (the caller all-reduces it together with its own data inside ``before_sync``)."""
+        into (the caller all-reduces it together with its own data inside ``before_sync``).
+        emission_factory: callable(y_ext, ma_neuron) -> object with ``loglik`` (default: Poisson EmissionOperands);
+        carry_in: [2,K] message in front of bin 0 of the recording (default: uniform, reference decoder.py:181-183)."""
         self.op = op
+        self.carry_in = carry_in
         self.K = op.K
         self.dev = y.device
         self.ma_neuron = ma_neuron
@@ -103,15 +108,22 @@ class EStep:
         self.adaptive = bool(adaptive) and self.halo > 0
         # tier 1 of the seam repair (conditional relaunch on the device); off = every repair is a host sweep
         self.device_repair = os.environ.get("PMG_DEVICE_REPAIR", "1") != "0"
-        self.halo_min = min(self.halo, DEFAULT_HALO_MIN)
+        self.halo_min = min(self.halo, DEFAULT_HALO_MIN)     # raised below once the chunk length is known
         if chunk_len is None:
             wide = em_mode and self.compact_ok and self.K > 31 * 8       # the 12-chain variants exist for K > 248
             chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count, EM_CHAINS_PER_SM if wide else 8,
                                     min_chunk=(min(MIN_CHUNK, 2 * self.halo) if self.adaptive else None))
         self.chunk_len = int(min(max(1, chunk_len), self.T_core))
+        # A seam that fails is repaired by re-running its chain: about one chunk of scan time at low occupancy,
+        # whatever the number of failing seams.  A shorter warm-up saves every chain `halo` steps at full occupancy.
+        # Halving the warm-up below ~chunk/5 cannot pay for even occasional repairs, so that is the floor.
+        floor = self.halo
+        while floor // 2 >= max(self.halo_min, self.chunk_len // 5) and floor // 2 >= 1:
+            floor //= 2
+        self.halo_min = min(self.halo, max(self.halo_min, floor))
         # common warm-up of this pass and of the next one (the pass writes the next pass's warm-start messages)
         self.halos = [self.halo, self.halo]
-        self._calm = 0
+        self._calm, self._streak = 0, 0
         self.plan = ops.make_plan(self.T, self.core.start, self.core.stop, self.chunk_len, self.halo,
                                   self.shard.is_first, self.shard.is_last, self.scale, halo_next=self.halo)
         S = self.plan.n_chain
@@ -122,12 +134,15 @@ class EStep:
         if ma_neuron is not None and ma_neuron.dim() == 2:
             ma_neuron, _, _ = self.shard.halo_exchange(ma_neuron.contiguous(), self.halo)
             self.ma_neuron = ma_neuron
-        self.em = ops.EmissionOperands(self.y, ma_neuron, impl=emission_impl, ones_col=True)
+        if emission_factory is not None:
+            self.em = emission_factory(self.y, ma_neuron)
+        else:
+            self.em = ops.EmissionOperands(self.y, ma_neuron, impl=emission_impl, ones_col=True)
         # fp16 counts for the statistics GEMM (the M-step uses the unmasked counts, reference core.py:807)
         if self.em.mode == 0:
             self.y16 = self.em.A16
         else:
-            self.y16 = ops.CountsF16(self.y, ones_col=True) if emission_impl == 0 else None
+            self.y16 = ops.CountsF16(self.y, ones_col=True) if (emission_impl == 0 and emission_factory is None) else None
         self.ll = torch.empty((self.T, self.K), **f32)
         self._alpha = None                 # [T,2,K] filtered posterior of the general path (allocated on first use)
         self._ax = None                    # [T,K+4] compact filtered posterior of the EM fast path
@@ -330,13 +345,19 @@ class EStep:
             return
         import numpy as np
         S = self.S
-        mass = n_fail > 0.1 * S * self.shard.world            # e.g. a nearly flat model: nothing forgets quickly
+        mass = n_fail > 0.25 * S * self.shard.world           # e.g. a nearly flat model: nothing forgets quickly
         if n_fail == 0:
             self._calm += 1
+            self._streak = 0
         else:
             self._calm = 0
-        if mass and nxt < self.halo:
+            self._streak += 1
+        if (mass or self._streak >= 4) and nxt < self.halo:
+            # repairs in four passes running (the per-chain boosts did not absorb them): this base is too short for
+            # this recording -- go back up and do not come down this far again
             new = min(self.halo, 2 * nxt)
+            self.halo_min = max(self.halo_min, new)
+            self._streak = 0
         elif self._calm >= 2 and nxt > self.halo_min:
             new = max(self.halo_min, nxt // 2)
             self._calm = 0
@@ -398,12 +419,12 @@ class EStep:
             sel = dict(sel_err=err_f, sel_tol=tol) if mode == 2 else {}
             ops.set_chain_halos(self.plan, *hf)
             if compact:
-                ops.forward_compact(self.plan, self.op, self.ll, self.ax,
+                ops.forward_compact(self.plan, self.op, self.ll, self.ax, carry_in=self.carry_in,
                                     halo_state=(self.halo_state if mode == 0 else None), fwd_end=self.fwd_end,
                                     first_out=self.first_out, mode=mode, chain_ids=ids,
                                     warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt], **sel)
                 return
-            ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr,
+            ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, carry_in=self.carry_in,
                         halo_state=(self.halo_state if mode == 0 else None), mode=mode, chain_ids=ids,
                         warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt], **sel)
 
@@ -450,6 +471,9 @@ class EStep:
         host_bad_f, host_bad_b = [], []
         err, any_f, any_b = self._verdict(before_sync)
         n_fix_f, n_fix_b = int(self.tail_host[T_FIX_F]), int(self.tail_host[T_FIX_B])
+        # seams still failing after the device repairs, over ALL ranks (what the warm-up planning may depend on:
+        # the common base must come out the same everywhere)
+        n_left = int(self.tail_host[T_FAIL_F]) + int(self.tail_host[T_FAIL_B])
         repaired = bool(any_f or any_b)
         # Host repair = parallel (Jacobi) sweeps: every chain whose incoming message is still off restarts,
         # all at once (on all ranks), from a snapshot of its neighbour's current boundary message; the
@@ -497,10 +521,14 @@ class EStep:
             self.warm_cur, self.warm_valid = nxt, True
         halo_used = self.halos[0]
         if self.adaptive:
-            e1 = self.err1_host
-            fail_f = torch.cat([torch.nonzero(~(e1[1:S] <= tol)).flatten() + 1] + host_bad_f).unique().numpy()
-            fail_b = torch.cat([torch.nonzero(~(e1[S:2 * S - 1] <= tol)).flatten()] + host_bad_b).unique().numpy()
-            self._adapt(n_fix_f + n_fix_b + n_relay_f + n_relay_b, fail_f, fail_b)
+            n_fail = n_fix_f + n_fix_b + n_left
+            if n_fail:
+                e1 = self.err1_host
+                fail_f = torch.cat([torch.nonzero(~(e1[1:S] <= tol)).flatten() + 1] + host_bad_f).unique().numpy()
+                fail_b = torch.cat([torch.nonzero(~(e1[S:2 * S - 1] <= tol)).flatten()] + host_bad_b).unique().numpy()
+            else:
+                fail_f = fail_b = _NO_CHAINS
+            self._adapt(n_fail, fail_f, fail_b)
         else:
             self._adapt(0, None, None)
 

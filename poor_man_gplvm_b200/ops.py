@@ -156,16 +156,22 @@ def emission_tile_n(K):
 
 
 def emission_prepare_f16(tuning, y16, ma_neuron=None, dt=1.0):
-    """(loglam16 [2,Kpad,ld16] fp16 hi/lo pieces, lam_sum[K])."""
+    """(loglam16 [2,Kpad,ld16] fp16 hi/lo pieces, lam_sum[K]).  The two buffers belong to `y16` and are reused by
+    every call with the same K (an EM iteration consumes them before the next one rewrites them, in stream order)."""
     lib = _lib.load()
     _f32(tuning, "tuning", 2)
     K, N = tuning.shape
     if N != y16.N:
         raise ValueError("y has %d neurons but tuning has %d" % (y16.N, N))
-    bn = emission_tile_n(K)
-    Kpad = (K + bn - 1) // bn * bn
-    L16 = torch.empty((2, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
-    lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
+    cache = getattr(y16, "_prep", None)
+    if cache is not None and cache[0] == K and cache[1].device == tuning.device:
+        _, L16, lam_sum, Kpad = cache
+    else:
+        bn = emission_tile_n(K)
+        Kpad = (K + bn - 1) // bn * bn
+        L16 = torch.empty((2, Kpad, y16.ld), dtype=torch.float16, device=tuning.device)
+        lam_sum = torch.empty(K, dtype=torch.float32, device=tuning.device)
+        y16._prep = (K, L16, lam_sum, Kpad)
     check(lib.pmg_emission_prepare_f16(K, N, _p(tuning), _p(ma_neuron), float(dt), Kpad, y16.ld, _p(L16),
                                        _p(lam_sum), _stream()), "pmg_emission_prepare_f16")
     _count(1)
@@ -276,6 +282,39 @@ class EmissionOperands:
         return emission_poisson(self.A, B, lam_sum, self.lgam, ma_latent, out=out)
 
 
+class GaussianEmission:
+    """Emission operand of the Gaussian families (reference decoder.py:50-57): same interface as EmissionOperands.
+    The observations are real-valued, so there is no fp16 copy (statistics and scans use the fp32 kernels)."""
+    mode = 0
+    A16 = None
+    tensor_cores = False
+
+    def __init__(self, y, ma_neuron=None, noise_std=0.5, impl=0, ones_col=False, dt_l=None):
+        _f32(y, "y", 2)
+        if dt_l is not None:
+            raise ValueError("per-bin dt is a Poisson option (reference decoder.py:73-85)")
+        self.y, self.ma, self.noise_std = y, ma_neuron, float(noise_std)
+        self.T, self.N = y.shape
+        if ma_neuron is not None:
+            _f32(ma_neuron, "ma_neuron")
+            if tuple(ma_neuron.shape) not in ((self.N,), (self.T, self.N)):
+                raise ValueError("ma_neuron must be [N] or [T,N]")
+
+    def loglik(self, tuning, ma_latent=None, dt=1.0, out=None):
+        lib = _lib.load()
+        _f32(tuning, "tuning", 2)
+        K = tuning.shape[0]
+        mu = tuning if dt == 1.0 else tuning * float(dt)
+        if out is None:
+            out = torch.empty((self.T, K), dtype=torch.float32, device=self.y.device)
+        ldm = self.N if (self.ma is not None and self.ma.dim() == 2) else 0
+        check(lib.pmg_emission_gaussian(self.T, self.N, K, _p(self.y), self.y.stride(0), _p(mu), _p(self.ma), ldm,
+                                        self.noise_std, _p(ma_latent), _p(out), out.stride(0), _stream()),
+              "pmg_emission_gaussian")
+        _count(1)
+        return out
+
+
 def naive_bayes_normalize(ll, inplace=False):
     """(log_post[T,K], lml_t[T]) (reference decoder.py:98-101)."""
     lib = _lib.load()
@@ -331,7 +370,11 @@ class MoveOperator:
             self.stationary = dev(stationary_joint(np.asarray(P0, dtype=np.float64), self.M.reshape(2, 2)))
 
     def cstruct(self):
-        s = PmgTransition()
+        """ctypes view of the operator (built once: the device arrays never move)"""
+        s = getattr(self, "_cs", None)
+        if s is not None:
+            return s
+        s = self._cs = PmgTransition()
         s.K, s.kind, s.W = self.K, self.kind, self.W
         s.taps = self.taps.data_ptr() if self.taps is not None else None
         s.inv_z = self.inv_z.data_ptr() if self.inv_z is not None else None

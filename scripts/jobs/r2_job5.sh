@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/j5_pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/j5_pytest_gpu.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/j5_bench.json 2> gpurun_out/j5_bench.err
+timeout 300 python bench.py --steps 20 --warmup 10 --bins 125000 --no-e2e --no-decode --no-cpu-baseline > gpurun_out/j5_bench_125k.json 2> gpurun_out/j5_bench_125k.err
+CMD="python bench.py --steps 2 --warmup 8 --no-e2e --no-decode --no-cpu-baseline --phase-steps 0"
+$CMD > gpurun_out/j5_plain.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 240 -c 160 --csv --log-file gpurun_out/j5_launches_headline.csv $CMD > gpurun_out/j5_ncu1.log 2>&1
+CMD2="python bench.py --steps 2 --warmup 12 --bins 125000 --no-e2e --no-decode --no-cpu-baseline --phase-steps 0"
+$CMD2 > gpurun_out/j5_plain2.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 160 --csv --log-file gpurun_out/j5_launches_125k.csv $CMD2 > gpurun_out/j5_ncu2.log 2>&1
+for k in emission_tc2_kernel fwd_c_kernel bwd_c_kernel atb_tc_kernel; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 1 -o gpurun_out/j5_prof_$k $CMD > gpurun_out/j5_ncufull_$k.log 2>&1
+done
+CMD3="python scripts/run_decode_once.py"
+$CMD3 > gpurun_out/j5_decode_plain.log 2>&1 && for k in atb_tc_kernel bwd_bulk_kernel fwd_bulk_kernel; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o gpurun_out/j5_profdec_$k $CMD3 > gpurun_out/j5_ncufulldec_$k.log 2>&1
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file gpurun_out/j5_launches_decode.csv $CMD3 > gpurun_out/j5_ncu3.log 2>&1
+tail -n 3 gpurun_out/j5_pytest_gpu.log

@@ -173,7 +173,7 @@ def test_adaptive_warm_up_shrinks_and_boosts(monkeypatch):
     monkeypatch.setenv("PMG_TEST_ADAPTIVE", "1")
     monkeypatch.setenv("PMG_HALO_MIN", "4")
     monkeypatch.setenv("PMG_TEST_FREEZE_AFTER", "3")
-    cfg = (1152, 12, 24, 32, 96, 12, 7)     # halo 32, chains of 96 bins, 12 passes; the tuning is converged from pass 3
+    cfg = (960, 12, 24, 32, 40, 12, 7)      # halo 32, chains of 40 bins, 12 passes; the tuning is converged from pass 3
     want = _oracle(cfg)
     got = _run(3, cfg)
     for i in range(cfg[5]):
