@@ -141,10 +141,14 @@ class EMLoop:
         mstep_fn(Phi, yw, tw, W) -> tuning [K,N] replaces the Adam M-step (updates W in place; Gaussian families)."""
         self.y = y_dev
         self.Phi = model._dev(tuning_basis)
-        self.W = model._dev(model.params).clone()
-        if self.W.shape != (self.Phi.shape[1], model.n_neuron):
-            raise ValueError("params shape %s does not match basis %s" % (tuple(self.W.shape), tuple(self.Phi.shape)))
-        self.state = ops.AdamState(self.W)
+        W0 = model._dev(model.params)
+        if W0.shape != (self.Phi.shape[1], model.n_neuron):
+            raise ValueError("params shape %s does not match basis %s" % (tuple(W0.shape), tuple(self.Phi.shape)))
+        # weights and Adam moments in one buffer: one copy snapshots / restores the optimiser
+        self.state = ops.AdamState.packed(W0)
+        self.W = self.state.W
+        self._snap = torch.empty_like(self.state.flat)
+        self._snap_count = torch.empty_like(self.state.count)
         # One buffer holds everything an EM iteration sums over ranks: the statistics [K, N+1] (column N =
         # sum_t gamma) followed by the E-step's record (log marginal, seam verdict) -> ONE all-reduce per iteration
         K_, N1 = op.K, model.n_neuron + 1
@@ -157,7 +161,9 @@ class EMLoop:
         self.broadcast_mstep = os.environ.get("PMG_MSTEP_BROADCAST", "0") != "0"
         self.prior_std, self.step_size, self.maxiter, self.tol = prior_std, step_size, maxiter, tol
         self._n_mstep = 0
+        self._row_len = 2 * int(maxiter) + 4            # loss history | gradient-norm history | final[2] | n_iter | pad
         self._hist = self._new_hist_block()
+        self._scratch = torch.zeros((2, self._row_len), dtype=torch.float32, device=self.W.device)
         self._tuning = torch.empty((2, self.Phi.shape[0], model.n_neuron), dtype=torch.float32, device=self.W.device)
         self._tuning_i = 0
         self._spec = None                  # M-step result enqueued ahead for the next iteration (see iteration)
@@ -188,28 +194,23 @@ class EMLoop:
 
     _HIST_BLOCK = 32
 
-    def _mstep_out(self):
-        """Output buffers of the next M-step.  Nothing that outlives an iteration is allocated per iteration:
-        a device allocation that misses the caching allocator is a driver call behind the process's memory-map
-        lock, which fit_em's background page-population of the host result buffers holds most of the time
-        (measured: sporadic 40-180 ms stalls of single EM iterations).  Two tuning buffers alternate; the Adam
-        histories live in blocks of _HIST_BLOCK iterations."""
-        slot = self._n_mstep % self._HIST_BLOCK
-        if slot == 0 and self._n_mstep > 0:
-            self._hist = self._new_hist_block()
-        self._n_mstep += 1
-        lh, eh, ni, fin = self._hist
-        self._tuning_i ^= 1
-        return lh[slot], eh[slot], ni[slot:slot + 1], fin[slot], self._tuning[self._tuning_i]
-
+    # ---- M-step plumbing.  The GPU work of "statistics + all-reduce + M-step" (`_mstep_enqueue`) touches only
+    # buffers fixed at construction, chosen by the parity of `_tuning_i`: tuning[p], the packed result row
+    # scratch[p], the optimiser state in place.  That makes it replayable inside a CUDA graph.  The bookkeeping
+    # that differs from iteration to iteration (history row, counters) is `_mstep_commit`, always eager.
     def _new_hist_block(self):
-        dev, n, mi = self.W.device, self._HIST_BLOCK, int(self.maxiter)
-        return (torch.empty((n, mi), dtype=torch.float32, device=dev), torch.empty((n, mi), dtype=torch.float32, device=dev),
-                torch.empty(n, dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.float32, device=dev))
+        return torch.empty((self._HIST_BLOCK, self._row_len), dtype=torch.float32, device=self.W.device)
 
-    def _stats_and_mstep(self, with_record=False):
-        """Sufficient statistics of the current posterior + the Adam M-step (reference core.py:807-810).
+    def _row_views(self, row):
+        """(loss_hist[maxiter], err_hist[maxiter], n_iter[1] int32, final[2]) inside one packed fp32 row"""
+        mi = int(self.maxiter)
+        return row[:mi], row[mi:2 * mi], row[2 * mi + 2:2 * mi + 3].view(torch.int32), row[2 * mi:2 * mi + 2]
+
+    def _mstep_enqueue(self, with_record=False):
+        """Sufficient statistics of the current posterior + the Adam M-step (reference core.py:807-810) into the
+        buffers of parity 1 - _tuning_i.  No Python state changes.
         with_record: the E-step's record behind the statistics is final and travels in the same all-reduce."""
+        p = 1 - self._tuning_i
         N = self.stats.shape[1] - 1
         if self.use_tc:
             # reference core.py:807; the ones column of the fp16 counts makes column N = sum_t gamma
@@ -220,21 +221,20 @@ class EMLoop:
         # time-sharded ranks: one all-reduce (fp32 on the wire, in place, no packing copies)
         self.shard.allreduce_flat_sum_(self.pack if with_record else self.pack[:self.stats.numel()])
         ops.phase("stats")
+        tun = self._tuning[p]
         if self.mstep_fn is not None:
-            self._tuning_i ^= 1
-            tun = self._tuning[self._tuning_i]
             tun.copy_(self.mstep_fn(self.Phi, self.stats[:, :N], self.stats[:, N], self.W))
-            ops.phase("mstep")
-            return (None, None, None, None, tun)
-        m_res = ops.mstep_adam(self.Phi, self.stats[:, :N], self.stats[:, N], self.W, self.state, self.prior_std,
-                               self.step_size, self.maxiter, self.tol, out=self._mstep_out())   # reference core.py:810
+        else:
+            lh, eh, ni, fin = self._row_views(self._scratch[p])
+            ops.mstep_adam(self.Phi, self.stats[:, :N], self.stats[:, N], self.W, self.state, self.prior_std,
+                           self.step_size, self.maxiter, self.tol, out=(lh, eh, ni, fin, tun))   # reference core.py:810
         if self.shard.active and self.broadcast_mstep:
             # The M-step is replicated: every rank runs the same deterministic kernel on the bit-identical result
             # of the all-reduce, so tuning and optimiser state agree bit for bit without communication (ranks
             # recompute their neighbours' halo bins and verify boundary seams at 1e-5; a divergence would show up
             # there).  PMG_MSTEP_BROADCAST=1 restores the explicit broadcast of rank 0's result (debugging).
             st = self.state
-            parts = [m_res[4], self.W, st.mu, st.nu]
+            parts = [tun, self.W, st.mu, st.nu]
             flat = torch.cat([t.reshape(-1) for t in parts] + [st.count.to(torch.float32)])
             self.shard.broadcast_(flat, 0)
             o = 0
@@ -244,7 +244,37 @@ class EMLoop:
                 o += n
             st.count.copy_(flat[o:o + 1].to(torch.int32))
         ops.phase("mstep")
-        return m_res
+
+    def _mstep_commit(self):
+        """Adopts the M-step `_mstep_enqueue` produced: flips the parity, files the result row in the history
+        (nothing that outlives an iteration is allocated per iteration: histories live in blocks of _HIST_BLOCK
+        rows) and returns (loss_hist, err_hist, n_iter, final, tuning) as device tensors."""
+        self._tuning_i ^= 1
+        p = self._tuning_i
+        tun = self._tuning[p]
+        if self.mstep_fn is not None:
+            return (None, None, None, None, tun)
+        slot = self._n_mstep % self._HIST_BLOCK
+        if slot == 0 and self._n_mstep > 0:
+            self._hist = self._new_hist_block()
+        self._n_mstep += 1
+        row = self._hist[slot]
+        row.copy_(self._scratch[p])
+        return self._row_views(row) + (tun,)
+
+    def _snapshot(self):
+        self._snap.copy_(self.state.flat)
+        self._snap_count.copy_(self.state.count)
+
+    def _rollback(self):
+        self.state.flat.copy_(self._snap)
+        self.state.count.copy_(self._snap_count)
+
+    def _spec_enqueue(self):
+        """GPU work enqueued behind an E-step's backward pass, before its verdict is known: snapshot of the
+        optimiser state, then the next iteration's statistics + M-step (with the E-step's record in the all-reduce)."""
+        self._snapshot()
+        self._mstep_enqueue(with_record=True)
 
     def iteration(self, want_gamma=False, want_dyn=False, want_gamma_lat=False, speculate=False):
         """want_gamma_lat: also return the fp32 latent posterior (always produced on the fp32 path).
@@ -253,36 +283,30 @@ class EMLoop:
         speculate=True: the statistics GEMM and the M-step of the NEXT iteration are enqueued right behind this
         iteration's backward pass, before the launching thread waits for the seam verdict, so the GPU has work
         while the host synchronises (the one synchronisation per EM iteration).  They only read what the
-        backward pass wrote; if a seam then fails and chains are re-run, the Adam state is restored from a
-        snapshot and the next iteration recomputes them.  Pass False for the last iteration of a fit."""
-        # (not right after an iteration that needed seam repairs: the next one probably does too, and a rolled
+        backward pass wrote; if a seam then fails and chains are re-run by the host, the optimiser state is restored
+        from a snapshot and the next iteration recomputes them.  Pass False for the last iteration of a fit.
+        In that steady state everything from the emission GEMM to the M-step is a fixed launch sequence on fixed
+        buffers: the E-step captures it into a CUDA graph (one per buffer parity and warm-up plan) and replays it."""
+        # (not right after an iteration that needed host repairs: the next one probably does too, and a rolled
         # back M-step is wasted work)
-        spec_ok = bool(speculate and self.use_tc and not self._last_repaired
+        spec_ok = bool(speculate and self.use_tc and not self._last_repaired and self.mstep_fn is None
                        and os.environ.get("PMG_NO_SPECULATE", "0") == "0")
         if self._spec is not None:
             m_res, self._spec = self._spec, None
         else:
-            m_res = self._stats_and_mstep()
-        nxt = {}
-
-        def enqueue_next():
-            st = self.state
-            nxt["snap"] = (self.W.clone(), st.mu.clone(), st.nu.clone(), st.count.clone(), self._n_mstep,
-                           self._hist, self._tuning_i)
-            nxt["m_res"] = self._stats_and_mstep(with_record=True)
-
+            self._mstep_enqueue()
+            m_res = self._mstep_commit()
         res = self.es.run(m_res[4], want_gamma=want_gamma, want_gamma_lat=(want_gamma_lat or not self.use_tc),
                           want_dyn=want_dyn, want_r=False, gamma16=self.gamma16,
-                          before_sync=enqueue_next if spec_ok else None)
+                          before_sync=self._spec_enqueue if spec_ok else None, graph_ok=spec_ok)
         self._last_repaired = bool(res.repaired)
         # GLM weights that produced THIS iteration's tuning (self.W may already hold the next M-step's result)
-        self.W_iter = nxt["snap"][0] if "m_res" in nxt else self.W
-        if "m_res" in nxt:
+        self.W_iter = self._snap[0] if spec_ok else self.W
+        if spec_ok:
             if res.repaired:
-                W, mu, nu, count, self._n_mstep, self._hist, self._tuning_i = nxt["snap"]
-                self.W.copy_(W); self.state.mu.copy_(mu); self.state.nu.copy_(nu); self.state.count.copy_(count)
+                self._rollback()
             else:
-                self._spec = nxt["m_res"]
+                self._spec = self._mstep_commit()
         self.gamma_lat = res.gamma_lat                             # reference core.py:668
         if res.tw is not None:
             self.tw = res.tw

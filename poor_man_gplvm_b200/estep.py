@@ -198,6 +198,12 @@ class EStep:
         # which seams exist: forward seam c sits in front of chain c; backward seam c behind chain c
         self.f_lo = 0 if not self.shard.is_first else 1
         self.b_hi = S if not self.shard.is_last else S - 1
+        # CUDA graphs of the steady-state E-step (+ whatever the caller enqueues in before_sync), see run()
+        # (time-sharded ranks capture their NCCL exchanges along; PMG_EM_GRAPH_DIST=0 keeps those runs eager)
+        self.use_graphs = (em_mode and os.environ.get("PMG_EM_GRAPH", "1") != "0" and self.dev.type == "cuda"
+                           and not self.shard.staged
+                           and (not self.shard.active or os.environ.get("PMG_EM_GRAPH_DIST", "0") != "0"))
+        self._graphs, self._graph_seen = {}, set()
         # host repair sweeps: same bound on every rank (block lengths, hence S, may differ between ranks)
         self.max_sweeps = self.shard.max_int(S, self.dev) * self.shard.world + 2
 
@@ -319,10 +325,10 @@ class EStep:
     def _lml_to_tail(self, lmr):
         self.tail[T_LML:T_LML + 1].copy_(lmr[self.core].sum(dim=0, keepdim=True, dtype=torch.float64))
 
-    def _verdict(self, before_sync=None):
-        """Brings the record (and the seam errors) to the host: the ONE synchronisation of an E-step.  On
-        time-sharded runs the record is summed over ranks -- inside the caller's collective when ``before_sync``
-        performs one (it must all-reduce ``self.tail``), else here."""
+    def _verdict_enqueue(self, before_sync=None):
+        """Enqueues what brings the record (and the seam errors) to the host.  On time-sharded runs the record is
+        summed over ranks -- inside the caller's collective when ``before_sync`` performs one (it must all-reduce
+        ``self.tail``), else here."""
         if before_sync is not None:
             before_sync()
         elif self.shard.active:
@@ -330,9 +336,38 @@ class EStep:
         self.tail_host.copy_(self.tail, non_blocking=True)
         self.err_host.copy_(self.err, non_blocking=True)
         self.err1_host.copy_(self.err1, non_blocking=True)
+
+    def _verdict_wait(self):
+        """The ONE synchronisation of an E-step."""
         torch.cuda.current_stream().synchronize()
         t = self.tail_host
         return self.err_host, bool(not (t[T_FAIL_F] == 0)), bool(not (t[T_FAIL_B] == 0))
+
+    def _verdict(self, before_sync=None):
+        self._verdict_enqueue(before_sync)
+        return self._verdict_wait()
+
+    def _replay_or_capture(self, key, enqueue):
+        """Steady-state E-steps are a fixed launch sequence on fixed buffers: the second time a configuration
+        (buffer parities, warm-up plan) comes up it is captured into a CUDA graph, from then on replayed -- one
+        launch instead of ~30 (the host, not the GPU, bounds short recordings and time-sharded ranks otherwise)."""
+        g = self._graphs.get(key)
+        if g is None:
+            if key not in self._graph_seen:
+                self._graph_seen.add(key)
+                enqueue()                                   # first sight: run it the plain way
+                return
+            if len(self._graphs) >= 16:                     # a drifting warm-up plan: stop hoarding graph memory
+                self._graphs.clear()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):    # (host I/O threads may be busy)
+                enqueue()
+            g.n_kernels = ops.LAUNCHES - n0                 # this library's kernels among the graph's nodes
+            self._graphs[key] = g
+        else:
+            ops._count(g.n_kernels)                         # replayed launches are launches
+        g.replay()
 
     def _adapt(self, n_fail, failed_f, failed_b):
         """Plans the warm-ups of the pass after next from this pass's record.  n_fail: seams repaired anywhere
@@ -382,7 +417,7 @@ class EStep:
         self.halos = [nxt, new]
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
-            before_sync=None, forward_only=False):
+            before_sync=None, forward_only=False, graph_ok=False):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
         the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes, the
         device repairs and the seam checks are enqueued, before the launching thread waits for the verdict (work
@@ -390,7 +425,10 @@ class EStep:
         ``self.tail`` with its own data; ``res.repaired`` tells whether chains were re-run by the HOST after it,
         i.e. whether what it read from this E-step's outputs was final).
         forward_only: emission + filter only (log marginal, one-step predictive marginals): what the batched callers
-        of the reference (model selection, shuffle tests) read from decode_latent."""
+        of the reference (model selection, shuffle tests) read from decode_latent.
+        graph_ok: the caller vouches that ``tuning``, ``gamma16`` and everything ``before_sync`` touches are fixed
+        buffers and that ``before_sync`` only enqueues GPU work (no Python state): the launch sequence may then be
+        captured into a CUDA graph and replayed."""
         S, K = self.S, self.K
         if forward_only:
             want_gamma = want_gamma_lat = want_dyn = want_r = False
@@ -399,8 +437,6 @@ class EStep:
         compact = (self.compact_ok and (gamma16 is not None or forward_only)
                    and not (want_gamma or want_gamma_lat or want_dyn or want_r))
         self.plan.halo, self.plan.halo_next = int(self.halos[0]), int(self.halos[1])
-        self.emission(tuning)
-        ops.phase("emission")
         gamma = torch.empty((self.T, 2, K), **f32) if want_gamma else None
         gamma_lat = torch.empty((self.T, K), **f32) if want_gamma_lat else None
         dyn = torch.empty((self.T, 2), **f32) if want_dyn else None
@@ -443,33 +479,46 @@ class EStep:
 
         seams = S > 1 or self.shard.active
         lmr = self.ax[:, K + 1] if compact else self.lmr
-        self.tail.zero_()
-        # ---- forward: all chains; seams between this rank's own chains are verified and repaired on the device
-        # (conditional relaunch) before anything consumes the filtered posterior; the boundary seam to the left
-        # neighbour rank is verified after the exchange (its repair, rare, is the host's)
-        fwd()
-        if S > 1 and self.device_repair:
-            self._check_fwd(compact, 1, True, self.tail[T_FIX_F:T_FIX_F + 1], err=self.err1)
-            fwd(mode=2)
-        self._exchange_fwd(compact, nxt)
-        if seams:
-            self._check_fwd(compact, self.f_lo, False, self.tail[T_FAIL_F:T_FAIL_F + 1])
-        self._lml_to_tail(lmr)
-        ops.phase("forward")
-        # ---- backward, same structure
-        if not forward_only:
-            bwd()
+
+        def enqueue():
+            self.emission(tuning)
+            ops.phase("emission")
+            self.tail.zero_()
+            # ---- forward: all chains; seams between this rank's own chains are verified and repaired on the
+            # device (conditional relaunch) before anything consumes the filtered posterior; the boundary seam to
+            # the left neighbour rank is verified after the exchange (its repair, rare, is the host's)
+            fwd()
             if S > 1 and self.device_repair:
-                self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1], err=self.err1)
-                bwd(mode=2)
-            self._exchange_bwd(nxt)
+                self._check_fwd(compact, 1, True, self.tail[T_FIX_F:T_FIX_F + 1], err=self.err1)
+                fwd(mode=2)
+            self._exchange_fwd(compact, nxt)
             if seams:
-                self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
-            ops.phase("backward")
+                self._check_fwd(compact, self.f_lo, False, self.tail[T_FAIL_F:T_FAIL_F + 1])
+            self._lml_to_tail(lmr)
+            ops.phase("forward")
+            # ---- backward, same structure
+            if not forward_only:
+                bwd()
+                if S > 1 and self.device_repair:
+                    self._check_bwd(S - 1, True, self.tail[T_FIX_B:T_FIX_B + 1], err=self.err1)
+                    bwd(mode=2)
+                self._exchange_bwd(nxt)
+                if seams:
+                    self._check_bwd(self.b_hi, False, self.tail[T_FAIL_B:T_FAIL_B + 1])
+                ops.phase("backward")
+            self._verdict_enqueue(before_sync)
+
+        if (graph_ok and self.use_graphs and compact and self.warm_valid and not forward_only and seams
+                and ops.PHASE_HOOK is None):
+            key = (cur, self.h_cur if self.adaptive else 0, int(self.halos[0]), int(self.halos[1]),
+                   tuning.data_ptr(), gamma16.data_ptr())
+            self._replay_or_capture(key, enqueue)
+        else:
+            enqueue()
 
         n_relay_f = n_relay_b = 0
         host_bad_f, host_bad_b = [], []
-        err, any_f, any_b = self._verdict(before_sync)
+        err, any_f, any_b = self._verdict_wait()
         n_fix_f, n_fix_b = int(self.tail_host[T_FIX_F]), int(self.tail_host[T_FIX_B])
         # seams still failing after the device repairs, over ALL ranks (what the warm-up planning may depend on:
         # the common base must come out the same everywhere)

@@ -634,6 +634,17 @@ class AdamState:
         self.mu = torch.zeros_like(params)
         self.nu = torch.zeros_like(params)
 
+    @classmethod
+    def packed(cls, params):
+        """State whose weights and moments are views of ONE buffer `flat` [3,B,N] = (W, mu, nu): a single copy
+        snapshots or restores the optimiser (the EM loop does that once per iteration)."""
+        st = cls.__new__(cls)
+        st.flat = torch.zeros((3,) + tuple(params.shape), dtype=torch.float32, device=params.device)
+        st.flat[0].copy_(params)
+        st.W, st.mu, st.nu = st.flat[0], st.flat[1], st.flat[2]
+        st.count = torch.zeros(1, dtype=torch.int32, device=params.device)
+        return st
+
 
 def mstep_adam(Phi, yw, tw, W, state, prior_std, step_size=0.01, maxiter=1000, tol=1e-6, min_iters=5,
                b1=0.9, b2=0.999, eps=1e-8, out=None):

@@ -4,9 +4,12 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/j5_pytest_gpu.log 2>&
 echo "pytest rc=$?" >> gpurun_out/j5_pytest_gpu.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/j5_bench.json 2> gpurun_out/j5_bench.err
 timeout 300 python bench.py --steps 20 --warmup 10 --bins 125000 --no-e2e --no-decode --no-cpu-baseline > gpurun_out/j5_bench_125k.json 2> gpurun_out/j5_bench_125k.err
-CMD="python bench.py --steps 2 --warmup 8 --no-e2e --no-decode --no-cpu-baseline --phase-steps 0"
+PMG_EM_GRAPH=0 timeout 300 python bench.py --steps 20 --warmup 10 --bins 125000 --no-e2e --no-decode --no-cpu-baseline > gpurun_out/j5_bench_125k_nograph.json 2> gpurun_out/j5_bench_125k_nograph.err
+PMG_EM_GRAPH=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-decode --no-cpu-baseline > gpurun_out/j5_bench_nograph.json 2> gpurun_out/j5_bench_nograph.err
+timeout 300 python bench.py --workload session --steps 30 --warmup 10 --no-decode --no-cpu-baseline > gpurun_out/j5_bench_session.json 2> gpurun_out/j5_bench_session.err
+CMD="env PMG_EM_GRAPH=0 python bench.py --steps 2 --warmup 8 --no-e2e --no-decode --no-cpu-baseline --phase-steps 0"
 $CMD > gpurun_out/j5_plain.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 240 -c 160 --csv --log-file gpurun_out/j5_launches_headline.csv $CMD > gpurun_out/j5_ncu1.log 2>&1
-CMD2="python bench.py --steps 2 --warmup 12 --bins 125000 --no-e2e --no-decode --no-cpu-baseline --phase-steps 0"
+CMD2="env PMG_EM_GRAPH=0 python bench.py --steps 2 --warmup 12 --bins 125000 --no-e2e --no-decode --no-cpu-baseline --phase-steps 0"
 $CMD2 > gpurun_out/j5_plain2.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 160 --csv --log-file gpurun_out/j5_launches_125k.csv $CMD2 > gpurun_out/j5_ncu2.log 2>&1
 for k in emission_tc2_kernel fwd_c_kernel bwd_c_kernel atb_tc_kernel; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 1 -o gpurun_out/j5_prof_$k $CMD > gpurun_out/j5_ncufull_$k.log 2>&1
