@@ -101,6 +101,9 @@ int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16, int64_t l
  */
 int pmg_naive_bayes_normalize(int64_t T, int K, const float* ll, int64_t ldll, float* log_post,
                               int64_t ldp, float* lml_t, pmg_stream_t stream);
+/* same, also writing post = exp(log_post) ([T, ldp]; core.py:517) in the one pass over the rows */
+int pmg_naive_bayes_posterior(int64_t T, int K, const float* ll, int64_t ldll, float* log_post, float* post,
+                              int64_t ldp, float* lml_t, pmg_stream_t stream);
 
 /* ------------------------------------------------------------- F1/F2, S1-S3 --
  * Forward filter (decoder.py:151-198) and backward smoother (decoder.py:200-332)
@@ -199,6 +202,12 @@ int pmg_backward_compact(const pmg_scan_plan* plan, const pmg_transition* tr, co
                          int64_t warm_stride, float* warm_out, void* gamma16, int64_t ldg,
                          float* beta_halo, float* beta_end, int mode, const int* chain_ids, int n_ids,
                          pmg_stream_t stream);
+
+/* dst[0] = sum_{i<n} src[i*stride], accumulated in fp64 in a fixed order (the log marginal of a pass is the sum of the
+ * one-step predictive log marginals, decoder.py:170,186).  workspace: pmg_strided_sum_workspace_bytes() bytes,
+ * 8-byte aligned, zeroed ONCE by the caller (the kernel re-arms it); one call at a time per workspace. */
+int64_t pmg_strided_sum_workspace_bytes(void);
+int pmg_strided_sum(int64_t n, const float* src, int64_t stride, float* dst, void* workspace, pmg_stream_t stream);
 
 /* ------------------------------------------------------------------ M1, S4 --
  * C[m,n] = sum_t A[t,m]*B[t,n]  (time is the reduction axis).  Used for the

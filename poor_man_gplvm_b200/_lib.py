@@ -56,6 +56,8 @@ SIGNATURES = {
                                            c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, c_stream]),
     "pmg_naive_bayes_normalize": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p,
                                             c_stream]),
+    "pmg_naive_bayes_posterior": (C.c_int, [C.c_int64, C.c_int, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p,
+                                            c_stream]),
     "pmg_forward": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
                               c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, c_i32p, C.c_int, c_stream]),
     "pmg_backward": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
@@ -79,6 +81,8 @@ SIGNATURES = {
                                  c_stream]),
     "pmg_seam_check_fix": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_float, C.c_float,
                                      C.c_int, c_f32p, c_f32p, c_stream]),
+    "pmg_strided_sum_workspace_bytes": (C.c_int64, []),
+    "pmg_strided_sum": (C.c_int, [C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_void_p, c_stream]),
     "pmg_atb_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "pmg_atb": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64,
                           C.c_void_p, C.c_int64, C.c_int, c_stream]),

@@ -573,12 +573,12 @@ class PoissonGPLVMJump1D:
             em = factory(y_dev, ma_n) if factory is not None else ops.EmissionOperands(y_dev, ma_n)
             dt = float(dt_dev[0].item()) if dt_dev.numel() else 1.0
         ll = em.loglik(self._dev(tuning), ma_l, dt)
-        log_post, lml = ops.naive_bayes_normalize(ll)
+        log_post, lml, post = ops.naive_bayes_normalize(ll, want_post=True)
         conv = (lambda t: t) if return_device else self._host
         return {'log_posterior_latent': conv(log_post),
                 'log_marginal_l': conv(lml),
                 'log_marginal_total': float(lml.sum(dtype=torch.float64).item()),
-                'posterior_latent': _rewrap_tsd(conv(torch.exp(log_post)), t_l),
+                'posterior_latent': _rewrap_tsd(conv(post), t_l),
                 'll_per_pos_l': conv(ll)}
 
     @_on_device

@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(256) emission_gaussian_kernel(int64_t T, int N
 
 // one warp per time bin: lml = logsumexp_k ll, log_post = ll - lml
 __global__ void nb_normalize_kernel(int64_t T, int K, const float* __restrict__ ll, int64_t ldll,
-                                    float* __restrict__ log_post, int64_t ldp, float* __restrict__ lml_t) {
+                                    float* __restrict__ log_post, int64_t ldp, float* __restrict__ lml_t,
+                                    float* __restrict__ post) {
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
   const int lane = threadIdx.x & 31;
@@ -275,7 +276,12 @@ __global__ void nb_normalize_kernel(int64_t T, int K, const float* __restrict__ 
   s = warp_sum(s);
   const float lml = logf(s) + m;
   float* orow = log_post + (size_t)t * ldp;
-  for (int k = lane; k < K; k += 32) orow[k] = row[k] - lml;
+  float* prow = post ? post + (size_t)t * ldp : nullptr;
+  for (int k = lane; k < K; k += 32) {
+    const float lp = row[k] - lml;
+    orow[k] = lp;
+    if (prow) prow[k] = expf(lp);            // posterior_latent = exp(log_posterior_latent), core.py:517
+  }
   if (lane == 0) lml_t[t] = lml;
 }
 
@@ -344,7 +350,17 @@ extern "C" int pmg_emission_poisson(int64_t T, int N, int K, const float* y, int
 extern "C" int pmg_naive_bayes_normalize(int64_t T, int K, const float* ll, int64_t ldll, float* log_post,
                                          int64_t ldp, float* lml_t, pmg_stream_t stream) {
   if (T <= 0 || K <= 0 || !ll || !log_post || !lml_t || ldll < K || ldp < K) return PMG_ERR_BAD_ARG;
-  pmg::nb_normalize_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, K, ll, ldll, log_post, ldp, lml_t);
+  pmg::nb_normalize_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, K, ll, ldll, log_post, ldp, lml_t,
+                                                                            nullptr);
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
+extern "C" int pmg_naive_bayes_posterior(int64_t T, int K, const float* ll, int64_t ldll, float* log_post,
+                                         float* post, int64_t ldp, float* lml_t, pmg_stream_t stream) {
+  if (T <= 0 || K <= 0 || !ll || !log_post || !post || !lml_t || ldll < K || ldp < K) return PMG_ERR_BAD_ARG;
+  pmg::nb_normalize_kernel<<<pmg::cdiv(T, 8), 256, 0, (cudaStream_t)stream>>>(T, K, ll, ldll, log_post, ldp, lml_t,
+                                                                            post);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

@@ -357,7 +357,8 @@ emission_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const bool wide = c0 + 32 <= BN;
         // the staging tile about to be overwritten must have been read by its TMA store
         if (lane == 0) {
-          if (p.ep_nbuf == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+          // at most ep_nbuf - 1 earlier stores may still be reading their staging tiles
+          if (p.ep_nbuf == 1) bulk_wait_read<0>(); else if (p.ep_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<2>();
         }
         __syncwarp();
         const uint32_t sb = stg + (uint32_t)buf * EP_BUF_BYTES;
@@ -577,7 +578,8 @@ emission_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         const bool wide = c0 + 32 <= BN;
         if (lane == 0) {
-          if (p.ep_nbuf == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
+          // at most ep_nbuf - 1 earlier stores may still be reading their staging tiles
+          if (p.ep_nbuf == 1) bulk_wait_read<0>(); else if (p.ep_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<2>();
         }
         __syncwarp();
         const uint32_t sb = stg + (uint32_t)buf * EP_BUF_BYTES;
@@ -873,13 +875,17 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   if (paired && pair_env && (BN % 16) == 0 && T >= 4 * TC_BM) {
     const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * (BN / 2) * TC_BK * 2;
     const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (size_t)((Kpad + 3) & ~3) * sizeof(float);
-    int nbuf = 2, stages = 0;
+    // staging tiles per epilogue warp vs pipeline stages (experiment knobs PMG_EM2_NBUF / PMG_EM2_STAGES)
+    static const int nbuf_env = std::getenv("PMG_EM2_NBUF") ? std::atoi(std::getenv("PMG_EM2_NBUF")) : 0;
+    static const int st2_env = std::getenv("PMG_EM2_STAGES") ? std::atoi(std::getenv("PMG_EM2_STAGES")) : 0;
+    int nbuf = nbuf_env >= 1 && nbuf_env <= 3 ? nbuf_env : 2, stages = 0;
     for (; nbuf >= 1; --nbuf) {
       const size_t stg_bytes = (size_t)8 * nbuf * EP_BUF_BYTES;
       stages = fixed + stg_bytes < smem_max ? (int)((smem_max - fixed - stg_bytes) / stage_bytes) : 0;
-      if (stages >= 3) break;
+      if (stages >= (nbuf_env ? 2 : 3)) break;
     }
     if (nbuf < 1) { nbuf = 1; }
+    if (st2_env >= 2 && stages > st2_env) stages = st2_env;
     if (stages >= 2) {
       if (stages > 6) stages = 6;
       EmissionTcParams p2 = p;
@@ -1130,6 +1136,47 @@ __global__ void split_bf16_kernel(int64_t T, int K, const float* __restrict__ sr
   }
 }
 
+// vectorised variant (K % 8 == 0, 16-byte aligned rows): 8 elements per thread, two 16-byte loads, two 16-byte stores
+// per piece; one warp-sized stripe of a row at a time.  HALF = 1: fp16 pieces, else bf16.
+template <int HALF>
+__global__ void __launch_bounds__(256) split_pieces_vec_kernel(int64_t T, int K8, const float* __restrict__ src,
+                                                               int64_t lds, uint16_t* __restrict__ dst, int64_t ld16) {
+  const int64_t total = T * (int64_t)K8;          // groups of 8 elements
+  const size_t piece = (size_t)T * ld16;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = g / K8;
+    const int k = (int)(g - t * K8) * 8;
+    const float4* sp = reinterpret_cast<const float4*>(src + (size_t)t * lds + k);
+    const float4 a = __ldcs(sp), b = __ldcs(sp + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (HALF) {
+        const __half h = __float2half_rn(v[e]);
+        hi[e] = __half_as_ushort(h);
+        lo[e] = __half_as_ushort(__float2half_rn(v[e] - __half2float(h)));
+      } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[e]);
+        hi[e] = __bfloat16_as_ushort(h);
+        lo[e] = __bfloat16_as_ushort(__float2bfloat16_rn(v[e] - __bfloat162float(h)));
+      }
+    }
+    uint4 H, L;
+    H.x = hi[0] | ((uint32_t)hi[1] << 16); H.y = hi[2] | ((uint32_t)hi[3] << 16);
+    H.z = hi[4] | ((uint32_t)hi[5] << 16); H.w = hi[6] | ((uint32_t)hi[7] << 16);
+    L.x = lo[0] | ((uint32_t)lo[1] << 16); L.y = lo[2] | ((uint32_t)lo[3] << 16);
+    L.z = lo[4] | ((uint32_t)lo[5] << 16); L.w = lo[6] | ((uint32_t)lo[7] << 16);
+    uint16_t* o = dst + (size_t)t * ld16 + k;
+    *reinterpret_cast<uint4*>(o) = H;
+    *reinterpret_cast<uint4*>(o + piece) = L;
+  }
+}
+
+static bool split_vec_ok(int K, const void* src, int64_t lds, const void* dst, int64_t ld16) {
+  return (K % 8) == 0 && K == ld16 && (lds % 4) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+}
+
 // posterior [T,K] fp32 -> two fp16 pieces [2][T][ld16] (hi + lo), zero padded
 __global__ void split_f16_kernel(int64_t T, int K, const float* __restrict__ src, int64_t lds,
                                  __half* __restrict__ dst, int64_t ld16) {
@@ -1173,7 +1220,10 @@ static void atb_tc_plan(int64_t T, int K, int N, int& BN, int& n_mtiles, int& n_
 extern "C" int pmg_split_f16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16,
                              pmg_stream_t stream) {
   if (T <= 0 || K <= 0 || !src || !dst16 || lds < K || ld16 < K || (ld16 & 7)) return PMG_ERR_BAD_ARG;
-  pmg::split_f16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(T, K, src, lds, (__half*)dst16, ld16);
+  if (pmg::split_vec_ok(K, src, lds, dst16, ld16))
+    pmg::split_pieces_vec_kernel<1><<<148 * 16, 256, 0, (cudaStream_t)stream>>>(T, K / 8, src, lds, (uint16_t*)dst16, ld16);
+  else
+    pmg::split_f16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(T, K, src, lds, (__half*)dst16, ld16);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }
@@ -1188,7 +1238,10 @@ extern "C" int64_t pmg_atb_f16_workspace_bytes(int64_t T, int K, int N) {
 extern "C" int pmg_split_bf16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16,
                               pmg_stream_t stream) {
   if (T <= 0 || K <= 0 || !src || !dst16 || lds < K || ld16 < K || (ld16 & 7)) return PMG_ERR_BAD_ARG;
-  pmg::split_bf16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(T, K, src, lds, (__nv_bfloat16*)dst16, ld16);
+  if (pmg::split_vec_ok(K, src, lds, dst16, ld16))
+    pmg::split_pieces_vec_kernel<0><<<148 * 16, 256, 0, (cudaStream_t)stream>>>(T, K / 8, src, lds, (uint16_t*)dst16, ld16);
+  else
+    pmg::split_bf16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(T, K, src, lds, (__nv_bfloat16*)dst16, ld16);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

@@ -662,51 +662,35 @@ __global__ void __launch_bounds__(256, 1) bwd_kernel(const BwdParams p) {
 // ============================================================================
 // tol >= 0: seams with !(err <= tol) are counted into *counter (if given) and, with fix != 0, their estimate is
 // overwritten by the truth: the snapshot a conditional restart (scan mode 2) of that chain starts from.
-__global__ void seam_check_kernel(int n, int len, float* est, int64_t ld_est, const float* truth,
-                                  int64_t ld_truth, float floor_val, float* err, float tol, int fix, float* counter) {
-  const int i = blockIdx.x;
+// One warp per seam (messages are 2K <= 8192 floats: two passes over L1-resident rows), 8 seams per CTA.
+__global__ void __launch_bounds__(256) seam_check_kernel(int n, int len, float* est, int64_t ld_est, const float* truth,
+                                                         int64_t ld_truth, float floor_val, float* err, float tol,
+                                                         int fix, float* counter) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
   float* a = est + (size_t)i * ld_est;
   const float* b = truth + (size_t)i * ld_truth;
-  __shared__ float sm[2][32];
-  __shared__ float tot[2];
   // messages are compared up to scale: normalise both to unit sum
   float sa = 0.f, sb = 0.f;
-  for (int j = threadIdx.x; j < len; j += blockDim.x) { sa += a[j]; sb += b[j]; }
+  for (int j = lane; j < len; j += 32) { sa += a[j]; sb += b[j]; }
   sa = warp_sum(sa); sb = warp_sum(sb);
-  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = sa; sm[1][threadIdx.x >> 5] = sb; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float ra = 0.f, rb = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ra += sm[0][w]; rb += sm[1][w]; }
-    tot[0] = ra; tot[1] = rb;
-  }
-  __syncthreads();
-  const float ia = 1.f / tot[0], ib = 1.f / tot[1];
+  const float ia = 1.f / sa, ib = 1.f / sb;
   float e = 0.f;
-  if (!(tot[0] > 0.f) || !(tot[1] > 0.f) || !(ia > 0.f) || !(ib > 0.f)) e = INFINITY;
-  for (int j = threadIdx.x; j < len; j += blockDim.x) {
+  if (!(sa > 0.f) || !(sb > 0.f) || !(ia > 0.f) || !(ib > 0.f)) e = INFINITY;
+  for (int j = lane; j < len; j += 32) {
     const float u = a[j] * ia, v = b[j] * ib;
     const float hi = fmaxf(u, v), lo = fminf(u, v);
     if (hi > floor_val) e = fmaxf(e, (hi - lo) / fmaxf(lo, 1e-37f));
     if (!(u == u) || !(v == v)) e = INFINITY;
   }
   e = warp_max(e);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sm[0][threadIdx.x >> 5] = e;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float r = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sm[0][w]);
-    err[i] = r;
-    tot[0] = r;
-    if (tol >= 0.f && !(r <= tol) && counter) atomicAdd(counter, 1.f);
+  if (lane == 0) {
+    err[i] = e;
+    if (tol >= 0.f && !(e <= tol) && counter) atomicAdd(counter, 1.f);
   }
-  if (tol >= 0.f && fix) {
-    __syncthreads();
-    if (!(tot[0] <= tol))
-      for (int j = threadIdx.x; j < len; j += blockDim.x) a[j] = b[j];
-  }
+  if (tol >= 0.f && fix && !(e <= tol))
+    for (int j = lane; j < len; j += 32) a[j] = b[j];
 }
 
 // ============================================================================
@@ -870,8 +854,8 @@ extern "C" int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, 
                               int64_t ld_truth, float floor_val, float* err, pmg_stream_t stream) {
   if (n <= 0) return PMG_OK;
   if (!est || !truth || !err || len <= 0) return PMG_ERR_BAD_ARG;
-  pmg::seam_check_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, len, const_cast<float*>(est), ld_est, truth, ld_truth,
-                                                              floor_val, err, -1.f, 0, nullptr);
+  pmg::seam_check_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(n, len, const_cast<float*>(est), ld_est, truth,
+                                                                        ld_truth, floor_val, err, -1.f, 0, nullptr);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }
@@ -881,8 +865,8 @@ extern "C" int pmg_seam_check_fix(int n, int len, float* est, int64_t ld_est, co
                                   pmg_stream_t stream) {
   if (n <= 0) return PMG_OK;
   if (!est || !truth || !err || len <= 0 || !(tol >= 0.f)) return PMG_ERR_BAD_ARG;
-  pmg::seam_check_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, len, est, ld_est, truth, ld_truth, floor_val, err,
-                                                              tol, fix, counter);
+  pmg::seam_check_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(n, len, est, ld_est, truth, ld_truth, floor_val,
+                                                                        err, tol, fix, counter);
   PMG_LAUNCH_CHECK();
   return PMG_OK;
 }

@@ -105,6 +105,51 @@ int pmg_atb_tc_launch(int64_t T, int M, int N, const float* A, int64_t lda, cons
                       float* C, int64_t ldc, void* ws, int64_t ws_bytes, cudaStream_t st);  // pmg_gemm_tc.cu
 int64_t pmg_atb_tc_workspace_bytes(int64_t T, int M, int N);
 
+namespace pmg {
+// dst[0] = sum_i src[i * stride] in fp64, fixed summation order: per-block partials, the last block to finish adds
+// them up in block order and re-arms the ticket.  (The log marginal of a pass = sum_t lmr_t, decoder.py:170,186.)
+constexpr int SS_BLOCKS = 128;
+__global__ void __launch_bounds__(256) strided_sum_kernel(int64_t n, const float* __restrict__ src, int64_t stride,
+                                                          float* __restrict__ dst, unsigned* ticket, double* part) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += (double)src[(size_t)i * stride];
+  acc = warp_sum_d(acc);
+  __shared__ double sm[8];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sm[w];
+    part[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile double*)part)[b];
+    dst[0] = (float)s;
+    *ticket = 0u;
+  }
+}
+}  // namespace pmg
+
+extern "C" int64_t pmg_strided_sum_workspace_bytes(void) { return 16 + 8 * pmg::SS_BLOCKS; }
+
+extern "C" int pmg_strided_sum(int64_t n, const float* src, int64_t stride, float* dst, void* workspace,
+                               pmg_stream_t stream) {
+  if (n <= 0 || !src || !dst || !workspace || stride < 1 || ((uintptr_t)workspace & 7)) return PMG_ERR_BAD_ARG;
+  int grid = (int)((n + 255) / 256);
+  if (grid > pmg::SS_BLOCKS) grid = pmg::SS_BLOCKS;
+  pmg::strided_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, src, stride, dst, (unsigned*)workspace,
+                                                                 (double*)((char*)workspace + 16));
+  PMG_LAUNCH_CHECK();
+  return PMG_OK;
+}
+
 extern "C" int64_t pmg_atb_workspace_bytes(int64_t T, int M, int N, int impl) {
   if (T <= 0 || M <= 0 || N <= 0) return 0;
   int64_t simt = (int64_t)pmg::atb_splits(T, M, N) * M * N * (int64_t)sizeof(float);

@@ -195,12 +195,15 @@ class EStep:
         if self.tail.numel() != TAIL or self.tail.dtype != torch.float32 or not self.tail.is_contiguous():
             raise ValueError("tail must be a contiguous float32 view of %d entries" % TAIL)
         self.tail_host = torch.zeros(TAIL, dtype=torch.float32).pin_memory()
+        self._sum_ws = None
         # which seams exist: forward seam c sits in front of chain c; backward seam c behind chain c
         self.f_lo = 0 if not self.shard.is_first else 1
         self.b_hi = S if not self.shard.is_last else S - 1
         # CUDA graphs of the steady-state E-step (+ whatever the caller enqueues in before_sync), see run()
         # (time-sharded ranks capture their NCCL exchanges along; PMG_EM_GRAPH_DIST=0 keeps those runs eager)
-        self.use_graphs = (em_mode and os.environ.get("PMG_EM_GRAPH", "1") != "0" and self.dev.type == "cuda"
+        # Opt-in (PMG_EM_GRAPH=1): measured on B200 the EM iteration is GPU-bound even at 125 000 bins per rank
+        # (1.32 ms eager vs 1.37 ms replayed), and every new warm-up plan costs a capture.
+        self.use_graphs = (em_mode and os.environ.get("PMG_EM_GRAPH", "0") != "0" and self.dev.type == "cuda"
                            and not self.shard.staged
                            and (not self.shard.active or os.environ.get("PMG_EM_GRAPH_DIST", "0") != "0"))
         self._graphs, self._graph_seen = {}, set()
@@ -210,7 +213,9 @@ class EStep:
     @property
     def alpha(self):
         if self._alpha is None:
-            self._alpha = torch.zeros((self.T, 2, self.K), dtype=torch.float32, device=self.dev)
+            # every row a pass reads is written first (core rows by the forward pass, the row behind the block by the
+            # boundary exchange): no 3.2 GB zero fill
+            self._alpha = torch.empty((self.T, 2, self.K), dtype=torch.float32, device=self.dev)
         return self._alpha
 
     @property
@@ -323,7 +328,9 @@ class EStep:
         return out
 
     def _lml_to_tail(self, lmr):
-        self.tail[T_LML:T_LML + 1].copy_(lmr[self.core].sum(dim=0, keepdim=True, dtype=torch.float64))
+        if self._sum_ws is None:
+            self._sum_ws = ops.strided_sum_workspace(self.dev)
+        ops.strided_sum(lmr[self.core], self.tail[T_LML:T_LML + 1], self._sum_ws)
 
     def _verdict_enqueue(self, before_sync=None):
         """Enqueues what brings the record (and the seam errors) to the host.  On time-sharded runs the record is
@@ -380,20 +387,24 @@ class EStep:
             return
         import numpy as np
         S = self.S
-        mass = n_fail > 0.25 * S * self.shard.world           # e.g. a nearly flat model: nothing forgets quickly
-        if n_fail == 0:
+        S_tot = S * self.shard.world
+        mass = n_fail > 0.25 * S_tot                          # e.g. a nearly flat model: nothing forgets quickly
+        # A repair pass re-runs the failing chains alone: ~one chunk of scan steps.  A warm-up step is paid by every
+        # chain.  While chunks are short compared with the warm-up, a few repairs per pass are the cheaper side.
+        few = n_fail <= max(1, S_tot // 100)
+        cheap = self.chunk_len <= 2 * nxt
+        if n_fail == 0 or (few and cheap):
             self._calm += 1
-            self._streak = 0
         else:
             self._calm = 0
-            self._streak += 1
+        self._streak = self._streak + 1 if (n_fail > 0 and not cheap) else 0
         if (mass or self._streak >= 4) and nxt < self.halo:
-            # repairs in four passes running (the per-chain boosts did not absorb them): this base is too short for
-            # this recording -- go back up and do not come down this far again
+            # expensive repairs in four passes running (the per-chain boosts did not absorb them): this base is too
+            # short for this recording -- go back up and do not come down this far again
             new = min(self.halo, 2 * nxt)
             self.halo_min = max(self.halo_min, new)
             self._streak = 0
-        elif self._calm >= 2 and nxt > self.halo_min:
+        elif self._calm >= 2 and nxt > self.halo_min and (n_fail == 0 or self.chunk_len <= nxt):
             new = max(self.halo_min, nxt // 2)
             self._calm = 0
         c, n = self.h_cur, 1 - self.h_cur
@@ -440,7 +451,11 @@ class EStep:
         gamma = torch.empty((self.T, 2, K), **f32) if want_gamma else None
         gamma_lat = torch.empty((self.T, K), **f32) if want_gamma_lat else None
         dyn = torch.empty((self.T, 2), **f32) if want_dyn else None
-        r = torch.zeros((self.T, 2, K), **f32) if want_r else None
+        r = None
+        if want_r:        # rows core.start+1 .. core.stop are written by the backward pass; row core.start is unused
+            r = torch.empty((self.T, 2, K), **f32)
+            r[:self.core.start + 1].zero_()
+            r[self.core.stop:].zero_()
 
         cur, nxt = self.warm_cur, 1 - self.warm_cur
         f_in = self.fwarm[cur] if self.warm_valid else getattr(self.op, "stationary", None)

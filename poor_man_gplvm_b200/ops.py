@@ -315,13 +315,19 @@ class GaussianEmission:
         return out
 
 
-def naive_bayes_normalize(ll, inplace=False):
-    """(log_post[T,K], lml_t[T]) (reference decoder.py:98-101)."""
+def naive_bayes_normalize(ll, inplace=False, want_post=False):
+    """(log_post[T,K], lml_t[T]) (reference decoder.py:98-101); want_post: also exp(log_post), in the same pass."""
     lib = _lib.load()
     _f32(ll, "ll", 2)
     T, K = ll.shape
     log_post = ll if inplace else torch.empty_like(ll)
     lml = torch.empty(T, dtype=torch.float32, device=ll.device)
+    if want_post:
+        post = torch.empty_like(ll)
+        check(lib.pmg_naive_bayes_posterior(T, K, _p(ll), K, _p(log_post), _p(post), K, _p(lml), _stream()),
+              "pmg_naive_bayes_posterior")
+        _count(1)
+        return log_post, lml, post
     check(lib.pmg_naive_bayes_normalize(T, K, _p(ll), K, _p(log_post), K, _p(lml), _stream()),
           "pmg_naive_bayes_normalize")
     _count(1)
@@ -511,6 +517,21 @@ def seam_check_fix(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, tol, fi
 
 
 # ----------------------------------------------------------------------------- reductions over time
+def strided_sum_workspace(device):
+    """zero-initialised scratch of pmg_strided_sum (one per caller: calls sharing it must be stream-ordered)"""
+    n = int(_lib.load().pmg_strided_sum_workspace_bytes())
+    return torch.zeros((n + 7) // 8, dtype=torch.int64, device=device)
+
+
+def strided_sum(src, dst, ws):
+    """dst[0] = sum(src) for a 1-D float32 view `src` (any stride), fp64 accumulation, one launch."""
+    if src.dim() != 1 or src.dtype != torch.float32 or dst.dtype != torch.float32:
+        raise TypeError("strided_sum expects a 1-D float32 view and a float32 destination")
+    check(_lib.load().pmg_strided_sum(int(src.shape[0]), _p(src), int(src.stride(0)) if src.shape[0] > 1 else 1, _p(dst),
+                                      _p(ws), _stream()), "pmg_strided_sum")
+    _count(1)
+
+
 _ws_cache = {}
 
 
