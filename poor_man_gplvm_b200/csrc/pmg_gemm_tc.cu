@@ -909,8 +909,17 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
       cfg.blockDim = dim3(EM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
       cfg.attrs = attr; cfg.numAttrs = 1;
       cfg.gridDim = dim3((unsigned)(sms & ~1));
-      int max_clusters = 0;
-      cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, emission_tc2_kernel, &cfg);
+      // (the occupancy query costs tens of microseconds of host time: once per shared-memory size)
+      static size_t occ_smem = 0;
+      static int occ_clusters = 0, occ_dev = -1;
+      static cudaError_t occ_err = cudaSuccess;
+      if (occ_smem != smem || occ_dev != dev) {
+        occ_dev = dev;
+        occ_err = cudaOccupancyMaxActiveClusters(&occ_clusters, emission_tc2_kernel, &cfg);
+        occ_smem = smem;
+      }
+      const int max_clusters = occ_clusters;
+      const cudaError_t oe = occ_err;
       const int n_units2 = ((p.n_mtiles + 2 * EM_MI - 1) / (2 * EM_MI)) * p.n_ntiles;
       if (oe == cudaSuccess && max_clusters >= 1) {
         int n_cl = max_clusters < n_units2 ? max_clusters : n_units2;

@@ -565,8 +565,16 @@ extern "C" int pmg_mstep_adam_ld(int K, int B, int N, const float* Phi, const fl
     PMG_CUDA_CHECK(cudaGetDevice(&dev_l));
     PMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms_l, cudaDevAttrMultiProcessorCount, dev_l));
     if (lag_env && smem_l <= 200 * 1024) {
-      PMG_CUDA_CHECK(cudaFuncSetAttribute(mstep_adam_lag_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-      PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_l, mstep_adam_lag_kernel<LT>, LT, smem_l));
+      // attribute + occupancy query once per shared-memory size (host time of a launch that runs every EM iteration)
+      static size_t cached_smem = 0;
+      static int cached_per = 0, cached_dev = -1;
+      if (cached_smem != smem_l || cached_dev != dev_l) {
+        cached_dev = dev_l;
+        PMG_CUDA_CHECK(cudaFuncSetAttribute(mstep_adam_lag_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+        PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per, mstep_adam_lag_kernel<LT>, LT, smem_l));
+        cached_smem = smem_l;
+      }
+      per_l = cached_per;
       if (per_l >= 1 && ntiles_l <= sms_l * per_l && ntiles_l <= 1024) {
         p.Bs = Bs_l; p.phi_in_smem = phi_l;
         unsigned* arrived = (unsigned*)((char*)workspace + 256 + (size_t)(maxiter + 1) * 1024 * 2 * sizeof(double));

@@ -189,8 +189,10 @@ class EStep:
             self.hb_host = [np.full(S, self.halo, np.int32), np.full(S, self.halo, np.int32)]
             self.boost_f, self.boost_b = np.zeros(S, np.int32), np.zeros(S, np.int32)
             self.h_cur = 0
-            # a boosted warm-up still starts inside the previous chain's processed bins (or the fetched halo rows)
-            self.boost_cap = max(self.halo, min(4 * self.halo, self.chunk_len + self.halo_min))
+            # A boosted chain runs longer than its neighbours and the pass ends with the longest chain, so a boost
+            # never exceeds the initial warm-up (the length every chain had before the base came down); a seam that
+            # still fails then is repaired on the device every pass.
+            self.boost_cap = self.halo
         self.tail = tail if tail is not None else torch.zeros(TAIL, **f32)
         if self.tail.numel() != TAIL or self.tail.dtype != torch.float32 or not self.tail.is_contiguous():
             raise ValueError("tail must be a contiguous float32 view of %d entries" % TAIL)
