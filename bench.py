@@ -68,8 +68,11 @@ def ncu_traffic():
                 def gb(x):
                     v, u = x.split()
                     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-                name = rec["kernel"].replace("void ", "").split("(")[0].split("<")[0]
-                out[name] = gb(rec["dram__bytes_read.sum"]) + gb(rec["dram__bytes_write.sum"])
+                full = rec["kernel"].replace("void ", "").split("(")[0]
+                name = full.split("<")[0]
+                val = gb(rec["dram__bytes_read.sum"]) + gb(rec["dram__bytes_write.sum"])
+                out[full.replace(" ", "")] = val              # e.g. atb_tc_kernel<1,0> (statistics) vs <2,1> (xi)
+                out.setdefault(name, val)
     except Exception:
         return {}
     return out
@@ -570,7 +573,7 @@ def run_ours(args):
     }
     kernel_of = {"forward": "fwd_c_kernel" if compact else "fwd_bulk_kernel",
                  "backward": "bwd_c_kernel" if compact else "bwd_bulk_kernel",
-                 "emission": "emission_tc_kernel", "stats": "atb_tc_kernel"}
+                 "emission": "emission_tc2_kernel", "stats": "atb_tc_kernel<1,0>"}
     traffic = ncu_traffic() if (args.workload == "headline" and not args.bins and world == 1) else {}
     roof_all = {}
     for name, (bound, amount, survey) in algo.items():

@@ -123,7 +123,7 @@ class EStep:
         self.halo_min = min(self.halo, max(self.halo_min, floor))
         # common warm-up of this pass and of the next one (the pass writes the next pass's warm-start messages)
         self.halos = [self.halo, self.halo]
-        self._calm, self._streak = 0, 0
+        self._calm, self._streak, self._hold, self._bounces = 0, 0, 0, 0
         self.plan = ops.make_plan(self.T, self.core.start, self.core.stop, self.chunk_len, self.halo,
                                   self.shard.is_first, self.shard.is_last, self.scale, halo_next=self.halo)
         S = self.plan.n_chain
@@ -400,13 +400,20 @@ class EStep:
         else:
             self._calm = 0
         self._streak = self._streak + 1 if (n_fail > 0 and not cheap) else 0
+        if self._hold:
+            self._hold -= 1
         if (mass or self._streak >= 4) and nxt < self.halo:
             # expensive repairs in four passes running (the per-chain boosts did not absorb them): this base is too
-            # short for this recording -- go back up and do not come down this far again
+            # short for the model as it is now -- go back up, wait before trying again (early EM iterations change the
+            # model quickly), and after three such bounces stop coming down this far
             new = min(self.halo, 2 * nxt)
-            self.halo_min = max(self.halo_min, new)
+            self._bounces += 1
+            self._hold = 6 * self._bounces
+            if self._bounces >= 3:
+                self.halo_min = max(self.halo_min, new)
             self._streak = 0
-        elif self._calm >= 2 and nxt > self.halo_min and (n_fail == 0 or self.chunk_len <= nxt):
+        elif (self._calm >= 2 and self._hold == 0 and nxt > self.halo_min
+              and (n_fail == 0 or self.chunk_len <= nxt)):
             new = max(self.halo_min, nxt // 2)
             self._calm = 0
         c, n = self.h_cur, 1 - self.h_cur

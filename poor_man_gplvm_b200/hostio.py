@@ -24,13 +24,27 @@ _pool = None
 _stream = {}
 
 
+def host_threads(want):
+    """Worker threads this process may use for host-side copies / page population: `want`, scaled down when several
+    ranks share the host (8 ranks x (6 staging + 8 populate threads) on one 32-core socket was round 1's e2e collapse
+    at 8 GPUs)."""
+    try:
+        import torch.distributed as dist
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    except Exception:
+        world = 1
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    cores = os.cpu_count() or 8
+    return max(2, min(int(want), cores // (2 * max(1, local))))
+
+
 def _staging():
     global _ring, _pool
     with _lock:
         if _ring is None:
             bufs = [torch.empty(_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(_NBUF)]
             _ring = [(b, b.numpy()) for b in bufs]
-            _pool = ThreadPoolExecutor(max_workers=_NBUF)
+            _pool = ThreadPoolExecutor(max_workers=host_threads(_NBUF))
     return _ring, _pool
 
 
@@ -124,7 +138,7 @@ class HostBuffers:
     device->host copies."""
 
     def __init__(self, specs, threads=None):
-        threads = threads or int(os.environ.get("PMG_TOUCH_THREADS", "8"))
+        threads = threads or host_threads(int(os.environ.get("PMG_TOUCH_THREADS", "8")))
         self._pool = ThreadPoolExecutor(max_workers=threads)
         self._arrays, self._futs = {}, {}
         for name, shape, dtype in specs:

@@ -164,11 +164,11 @@ def test_bench_reads_ncu_traffic_from_the_committed_profile():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     tr = bench.ncu_traffic()
-    for k in ("emission_tc_kernel", "atb_tc_kernel", "fwd_c_kernel", "bwd_c_kernel"):
+    for k in ("emission_tc2_kernel", "atb_tc_kernel<1,0>", "atb_tc_kernel<2,1>", "fwd_c_kernel", "bwd_c_kernel"):
         assert k in tr, (k, sorted(tr))
         assert 1e9 < tr[k] < 2e10
     # emission moves its compulsory bytes (1 GB of fp16 counts in, 1.6 GB of ll out) and little more
-    assert 2.4e9 < tr["emission_tc_kernel"] < 3.0e9
+    assert 2.4e9 < tr["emission_tc2_kernel"] < 3.0e9
 
 
 def test_clock_sampler_parses_nvidia_smi_lines():
