@@ -99,13 +99,17 @@ def e_step(y, tuning, P, M, ma_neuron, ma_latent, likelihood_scale=1.0, dtype=np
 
 
 def fit_em_linear(model, y, hyperparam={}, n_iter=20, log_posterior_init=None, ma_neuron=None, ma_latent=None,
-                  likelihood_scale=1.0, m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6):
+                  likelihood_scale=1.0, m_step_step_size=0.01, m_step_maxiter=1000, m_step_tol=1e-6,
+                  m_step_schedule=None):
     """The reference EM driver (core.py:592-713, :802-849) with the restated M-step of ``ref_numpy`` and the
     E-step in linear space (``e_step`` above) instead of the per-step log-space joint.  The log-space restatement
     costs 4K^2 exponentials per bin; this one two K x K mat-vecs, which is what makes parity runs at the real
     shapes (K=400 / K=2000, thousands of bins) affordable.  ``model``: an ``OraclePoissonGPLVMJump1D`` in
     fp64.  PINNED through ``tests/test_oracle_golden.py::test_linear_em_driver_matches_reference_source``: it
-    reproduces the reference source's README run (golden fixture) to 1e-9."""
+    reproduces the reference source's README run (golden fixture) to 1e-9.
+    ``m_step_schedule``: optional list of Adam step counts, one per EM iteration, that replaces the stopping rule
+    (``n_iter`` of that M-step is pinned: maxiter = the count, tol = -1) -- the stopping step of the default rule is
+    decided by a relative loss change of 1e-6, i.e. by rounding, so implementations are compared step for step."""
     from . import ref_numpy as ref
     fd = np.float64
     y_ = np.asarray(y, dtype=fd)
@@ -120,10 +124,11 @@ def fit_em_linear(model, y, hyperparam={}, n_iter=20, log_posterior_init=None, m
     lp_curr = np.asarray(log_posterior_init, dtype=fd)
     opt_state = ref.adam_init(params)
     lml_l, n_it, losses = [], [], []
-    for _ in range(n_iter):
+    for it in range(n_iter):
         yw, tw = ref.get_statistics(lp_curr, y_)
+        mi, tl = (m_step_maxiter, m_step_tol) if m_step_schedule is None else (int(m_step_schedule[it]), -1.0)
         m_res = ref.adam_run(params, opt_state, prior_std, basis, yw, tw, step_size=m_step_step_size,
-                             maxiter=m_step_maxiter, tol=m_step_tol)
+                             maxiter=mi, tol=tl)
         params, opt_state = m_res["params"], m_res["opt_state"]
         n_it.append(int(m_res["n_iter"])); losses.append(float(m_res["final_loss"]))
         tuning = ref.get_tuning_softplus(params, basis)

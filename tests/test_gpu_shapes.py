@@ -134,12 +134,15 @@ def test_session_shape_default_adam():
     rel = np.abs(lg - lw) / np.abs(lw)
     same = n_got == n_want
     assert np.all(rel[same] < 1e-4) and np.all(rel < 3e-3) and rel[-1] < 1e-4, (lg, lw, n_got, n_want)
-    # different stopping steps leave the tuning within the optimiser's own tolerance, not within 1e-3 (the reference's
-    # own fp32 and fp64 runs differ by 1.7e-2 on the README example, test_gpu_golden.py): compared on the scale of a
-    # typical rate, and through what the tuning is for -- the expected counts it predicts
-    d_t = np.abs(got["tuning"] - want["tuning"])
-    assert np.max(d_t / (want["tuning"] + 0.05)) < 0.1 and np.mean(d_t / want["tuning"]) < 5e-3
-    assert np.mean(np.abs(got["posterior_latent_marg"] - want["posterior_latent_marg"])) < 1e-3
+    # Different stopping steps leave the tuning within the optimiser's own tolerance, not within 1e-3 (the reference's
+    # own fp32 and fp64 runs differ by 1.7e-2 on the README example, test_gpu_golden.py).  So the oracle is run once
+    # more with the Adam step counts the GPU fit chose (teacher-forced stopping steps): everything is then held to
+    # the north-star tolerances.
+    want = lin.fit_em_linear(oracle, d["y"], m_step_schedule=[int(n) for n in n_got], **kw)
+    lw = np.array(want["log_marginal_l"])
+    assert np.max(np.abs(lg - lw) / np.abs(lw)) < 1e-4, (lg, lw)
+    assert np.max(np.abs(got["tuning"] - want["tuning"]) / want["tuning"]) < 1e-3
+    assert np.max(np.abs(got["posterior_latent_marg"] - want["posterior_latent_marg"])) < 5e-5
 
 
 def test_naive_bayes_config_c_shape():

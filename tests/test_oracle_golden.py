@@ -132,3 +132,23 @@ def test_linear_em_driver_matches_reference_source():
     assert np.allclose(em["tuning"], g["em_tuning"], rtol=1e-6)
     assert np.allclose(em["posterior"], g["em_posterior"], rtol=0, atol=1e-7)      # fixture stored in float32
     assert em["m_step_n_iter"] == [int(v) for v in g["em_m_n_iter"]]
+
+
+def test_linear_em_driver_step_schedule_reproduces_the_free_run():
+    """``m_step_schedule`` pins each M-step's Adam step count (what the real-shape GPU tests use to compare fits
+    whose default stopping rule would otherwise be decided by rounding): fed the counts of the reference source's
+    default-Adam README run, the driver must land on that run's results."""
+    from oracle import linear_ref as lin
+    g, c = load("readme_default", "f64")
+    o = make_oracle(g, c, np.float64)
+    kw = em_kwargs(g, c)
+    kw.pop("n_time_per_chunk")
+    for k in ("m_step_maxiter", "m_step_tol"):
+        kw.pop(k, None)
+    n = 4
+    kw["n_iter"] = n
+    em = lin.fit_em_linear(o, g["in_y"].astype(np.float64), m_step_schedule=[int(v) for v in g["em_m_n_iter"][:n]], **kw)
+    assert em["m_step_n_iter"] == [int(v) for v in g["em_m_n_iter"][:n]]
+    # (hundreds of Adam steps per M-step amplify the last-digit differences between the linear-space E-step and the
+    # reference's log-space one: 3e-9 here, 1e-9 on the pinned 50-step run above)
+    assert np.allclose(np.array(em["log_marginal_l"]), g["em_log_marginal_l"][:n], rtol=1e-7)
