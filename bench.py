@@ -37,7 +37,10 @@ WORKLOADS = {
     "readme": (30, 100, 1000, 10.0, 1.0),
     "session": (200, 100, 100000, 10.0, 1.0),
     "headline": (500, 400, 1000000, 10.0, 1.0),
-    "stress": (300, 2000, 1000000, 10.0, 1.0),
+    "stress": (300, 2000, 1000000, 10.0, 1.0),          # K = 2000 with the default (11-tap) move kernel
+    # BASELINE configs[4] as written: a DENSE K x K move kernel (custom_transition_kernel, gp_kernel.py:61-66)
+    # dominating the scan -> the lockstep tensor-core scan (pmg_forward_dense / pmg_backward_dense)
+    "stress_dense": (300, 2000, 1000000, 10.0, 1.0),
     "nb": (1000, 200, 10000000, 10.0, 1.0),
 }
 METRIC = "EM time-bins x iters/s"
@@ -84,13 +87,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
+    PERIOD_MS = 20
+
     def __init__(self, index=0):
         self.index, self.proc = index, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -415,7 +420,11 @@ def run_ours(args):
     if args.bins:
         T = args.bins
     strong = args.scaling == "strong"
-    model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, movement_variance=mv, device=dev)
+    mk = {}
+    if args.workload == "stress_dense":
+        xk = np.arange(K, dtype=np.float64)
+        mk["custom_transition_kernel"] = (np.exp(-np.abs(xk[:, None] - xk[None, :]) / 150.0) + 0.02).astype(np.float32)
+    model = pmg.PoissonGPLVMJump1D(N, K, tuning_lengthscale=ls, movement_variance=mv, device=dev, **mk)
     rng = np.random.default_rng(1)
     model.params = rng.standard_normal((model.n_basis, N)).astype(np.float32)
     P, logP, M, logM, op = model._transition_pack({})
@@ -565,6 +574,7 @@ def run_ours(args):
     # bytes per bin -- reported beside as "survey_bytes".  GEMMs: one fp32-equivalent GEMM, 2*T*N*K flop.
     compact = bool(loop.es.compact_ok and loop.use_tc)
     Tr = T_rank
+    dense = getattr(op, "dense", None) is not None
     algo = {
         "forward": ("hbm", (8.0 * K + 16.0) * Tr if compact else 12.0 * K * Tr, 12.0 * K * Tr),
         "backward": ("hbm", 12.0 * K * Tr if compact else 16.0 * K * Tr, 20.0 * K * Tr),
@@ -574,6 +584,11 @@ def run_ours(args):
     kernel_of = {"forward": "fwd_c_kernel" if compact else "fwd_bulk_kernel",
                  "backward": "bwd_c_kernel" if compact else "bwd_bulk_kernel",
                  "emission": "emission_tc2_kernel", "stats": "atb_tc_kernel<1,0>"}
+    if dense:
+        # lockstep scan: one K x K mat-vec per bin and pass = 2 K^2 fp32-equivalent flop (the warm-up bins and the
+        # three fp16-piece products that realise one fp32-grade product are overhead, not algorithmic work)
+        algo["forward"] = algo["backward"] = ("tensor", 2.0 * K * K * Tr, None)
+        kernel_of["forward"] = kernel_of["backward"] = "dense_step_gemm_kernel (+ dense_*_update_kernel)"
     traffic = ncu_traffic() if (args.workload == "headline" and not args.bins and world == 1) else {}
     roof_all = {}
     for name, (bound, amount, survey) in algo.items():
@@ -686,6 +701,9 @@ def run_ours(args):
                                           "all-reduce per EM iteration (K*(N+1) statistics + log marginal + seam "
                                           "verdict, fp32), replicated M-step" % world,
                            "l2": "inputs larger than L2 (y, ll, alpha, gamma each >= 0.1 GB per rank)",
+                           "move_kernel": ("dense custom_transition_kernel exp(-|dx|/150)+0.02, row-normalised; scan = "
+                                           "lockstep tcgen05 GEMM per time step over all chains" if dense else
+                                           "default RBF, band half width %d" % op.W),
                            "n_chain": loop.es.plan.n_chain, "chunk_len": loop.es.chunk_len,
                            "halo_per_iter": halos, "seam_repairs_on_device_in_timed_region": fixes,
                            "seam_relays_by_host_in_timed_region": relays, "adam_steps_per_iter": n_adam},
@@ -715,6 +733,7 @@ def main():
     ap.add_argument("--cpu-sample-bins", type=int, default=0,
                     help="bins per step of the CPU arm (default: 2000 for the in-line baseline, sized to a ~3 minute "
                          "run for --impl reference)")
+    ap.add_argument("--clocks-ms", type=int, default=20, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
@@ -722,6 +741,7 @@ def main():
     ap.add_argument("--phase-steps", type=int, default=None,
                     help="EM iterations of the instrumented (per-phase events) pass after the timed region")
     args = ap.parse_args()
+    ClockSampler.PERIOD_MS = max(5, args.clocks_ms)
     if args.impl == "reference":
         run_reference(args)
     else:

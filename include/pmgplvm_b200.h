@@ -203,6 +203,32 @@ int pmg_backward_compact(const pmg_scan_plan* plan, const pmg_transition* tr, co
                          float* beta_halo, float* beta_end, int mode, const int* chain_ids, int n_ids,
                          pmg_stream_t stream);
 
+/* Dense / wide-band move kernels (gp_kernel.py:61-66 custom_transition_kernel; :14-20 with a large
+ * movement_variance; BASELINE configs[4]) on the tensor cores: all chains advance in LOCKSTEP, so the n_chain
+ * mat-vecs of one time step are one [n_chain x K] . [K x K] GEMM (tcgen05 kind::f16, both operands as two fp16
+ * pieces under exact power-of-two scales, three products, fp32 accumulation), followed by a per-chain row kernel
+ * (likelihood factor, rank-1 jump term, normaliser, outputs, seam / warm-start messages).  Same chain, warm-up
+ * and output conventions as pmg_forward / pmg_backward, mode 0 only (repairs go through those).
+ * P16: device fp16 [2 directions][2 pieces][Kn][Kk] (256-byte aligned) with, for the row-normalised move matrix P0,
+ *      direction 0 (forward):  B[x', x] = 2^14 * P0[x, x'],  direction 1 (backward): B[x, x'] = 2^14 * P0[x, x'],
+ *      piece 0 = fp16(B), piece 1 = fp16(B - piece 0), zero padding; (Kk, Kn) from pmg_dense_scan_geometry.
+ * kb_ranges: HOST int32 [2 directions][n_ntiles][2] = first / one-past-last 64-column block that holds a non-zero
+ *      of rows [i*BN, (i+1)*BN) of B (band structure; NULL = all blocks).
+ * halo_max: upper bound of plan->halo_arr (ignored without per-chain warm-ups); a pass is halo_max + chunk_len steps.
+ * workspace: pmg_dense_scan_workspace_bytes(n_chain, K) bytes, 256-byte aligned. */
+int pmg_dense_scan_geometry(int K, int* Kk, int* Kn, int* BN, int* n_ntiles);
+int64_t pmg_dense_scan_workspace_bytes(int n_chain, int K);
+int pmg_forward_dense(const pmg_scan_plan* plan, const pmg_transition* tr, const void* P16, const int* kb_ranges,
+                      int halo_max, const float* ll, int64_t ldll, const float* carry_in, const float* warm_in,
+                      int64_t warm_stride, float* warm_out, float* alpha, float* lmr, float* halo_state,
+                      void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
+int pmg_backward_dense(const pmg_scan_plan* plan, const pmg_transition* tr, const void* P16, const int* kb_ranges,
+                       int halo_max, const float* ll, int64_t ldll, const float* alpha, const float* beta_in,
+                       const float* warm_in, int64_t warm_stride, float* warm_out, float* gamma, float* gamma_lat,
+                       void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial,
+                       float* beta_halo, float* beta_end, void* workspace, int64_t workspace_bytes,
+                       pmg_stream_t stream);
+
 /* dst[0] = sum_{i<n} src[i*stride], accumulated in fp64 in a fixed order (the log marginal of a pass is the sum of the
  * one-step predictive log marginals, decoder.py:170,186).  workspace: pmg_strided_sum_workspace_bytes() bytes,
  * 8-byte aligned, zeroed ONCE by the caller (the kernel re-arms it); one call at a time per workspace. */

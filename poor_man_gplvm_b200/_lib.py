@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpmgplvm_b200.so")
 
 c_f32p = C.c_void_p   # device pointers travel as integers
 c_i32p = C.c_void_p
+c_i32p_host = C.POINTER(C.c_int)   # host int arrays / out-parameters
 c_stream = C.c_void_p
 
 
@@ -63,6 +64,15 @@ SIGNATURES = {
     "pmg_backward": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
                                c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                C.c_int, c_i32p, C.c_int, c_stream]),
+    "pmg_dense_scan_geometry": (C.c_int, [C.c_int, c_i32p_host, c_i32p_host, c_i32p_host, c_i32p_host]),
+    "pmg_dense_scan_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "pmg_forward_dense": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), C.c_void_p, c_i32p_host,
+                                    C.c_int, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p,
+                                    c_f32p, C.c_void_p, C.c_int64, c_stream]),
+    "pmg_backward_dense": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), C.c_void_p, c_i32p_host,
+                                     C.c_int, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p,
+                                     c_f32p, C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+                                     C.c_void_p, C.c_int64, c_stream]),
     "pmg_scan_compact_supported": (C.c_int, [C.POINTER(PmgTransition), C.c_float]),
     "pmg_forward_compact": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
                                       c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int,

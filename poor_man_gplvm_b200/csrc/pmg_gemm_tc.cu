@@ -15,7 +15,6 @@
 #include "pmg_common.cuh"
 #include "pmg_tc.cuh"
 #include <cuda_bf16.h>
-#include <cstdlib>
 
 namespace pmg {
 
@@ -778,10 +777,7 @@ static uint32_t pow2_cols(int c) {
 // BN = accumulator columns per tile: K split into ceil(K/256) tiles, rounded up to 16
 extern "C" int pmg_emission_tile_n(int K) {
   if (K <= 0) return 0;
-  int nt = (K + 255) / 256;
-  // experiment knob: more, narrower column tiles (smaller pipeline stages)
-  static const int nt_env = std::getenv("PMG_EM_NT") ? std::atoi(std::getenv("PMG_EM_NT")) : 0;
-  if (nt_env > nt) nt = nt_env;
+  const int nt = (K + 255) / 256;
   int bn = (K + nt - 1) / nt;
   bn = (bn + 15) / 16 * 16;
   return bn;
@@ -849,15 +845,10 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   p.n_kblocks = (int)((ld16 + TC_BK - 1) / TC_BK);
   p.n_mtiles = (int)((T + TC_BM - 1) / TC_BM);
   p.n_ntiles = n_ntiles;
-  // experiment knobs (environment): PMG_EM_KERNEL=1 forces the single-tile kernel, PMG_EM_STAGES caps the pipeline
-  // depth, PMG_EM_STAGGER=1 enables the per-CTA K-block rotation (changes the low bits of ll, see below)
-  static const int kver_env = std::getenv("PMG_EM_KERNEL") ? std::atoi(std::getenv("PMG_EM_KERNEL")) : 2;
-  static const int st_env = std::getenv("PMG_EM_STAGES") ? std::atoi(std::getenv("PMG_EM_STAGES")) : 0;
-  // default 0: every tile accumulates the neuron blocks in the same order, so ll[t,:] is bit-identical wherever
-  // bin t sits in the launch -- time-sharded ranks recompute their neighbours' halo bins and their seam checks
-  // compare messages at 1e-5 (a rotated order changes ll by ~3e-5 absolute, i.e. the likelihood by 3e-5 relative)
-  static const int stagger_env = std::getenv("PMG_EM_STAGGER") ? std::atoi(std::getenv("PMG_EM_STAGGER")) : 0;
-  p.stagger = stagger_env;
+  // no per-CTA rotation of the K-block order: every tile accumulates the neuron blocks in the same order, so
+  // ll[t,:] is bit-identical wherever bin t sits in the launch -- time-sharded ranks recompute their neighbours'
+  // halo bins and their seam checks compare messages at 1e-5 (a rotated order changes ll by ~3e-5 absolute)
+  p.stagger = 0;
   p.idesc = make_idesc_f16(TC_BM, BN, 0, 0, 0);
   p.tmem_cols = pow2_cols(2 * BN);
   p.lam_sum = lam_sum; p.lgam = lgam; p.ma_latent = ma_latent; p.ll = ll; p.ldll = ldll;
@@ -869,23 +860,20 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
   const size_t smem_max = 227 * 1024;
 
   // 256-row work units + TMA-store epilogue: needs 16-byte aligned rows of ll
-  bool paired = kver_env != 1 && (ldll & 3) == 0 && ((uintptr_t)ll & 15) == 0;
+  bool paired = (ldll & 3) == 0 && ((uintptr_t)ll & 15) == 0;
   // CTA pairs (cta_group::2): 512-row units, every log-rate tile shared by the two SMs of a TPC
-  static const int pair_env = std::getenv("PMG_EM_PAIR") ? std::atoi(std::getenv("PMG_EM_PAIR")) : 1;
-  if (paired && pair_env && (BN % 16) == 0 && T >= 4 * TC_BM) {
+  if (paired && (BN % 16) == 0 && T >= 4 * TC_BM) {
     const uint32_t stage_bytes = EM_MI * TC_A_BYTES + EM_PB * (BN / 2) * TC_BK * 2;
     const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + (size_t)((Kpad + 3) & ~3) * sizeof(float);
-    // staging tiles per epilogue warp vs pipeline stages (experiment knobs PMG_EM2_NBUF / PMG_EM2_STAGES)
-    static const int nbuf_env = std::getenv("PMG_EM2_NBUF") ? std::atoi(std::getenv("PMG_EM2_NBUF")) : 0;
-    static const int st2_env = std::getenv("PMG_EM2_STAGES") ? std::atoi(std::getenv("PMG_EM2_STAGES")) : 0;
-    int nbuf = nbuf_env >= 1 && nbuf_env <= 3 ? nbuf_env : 2, stages = 0;
+    // staging tiles per epilogue warp vs pipeline stages: two tiles unless that leaves fewer than three stages
+    // (measured at the headline shape: 2 tiles / 3 stages 0.75 ms; forcing 2 or 3 tiles with 2 stages 0.83 ms)
+    int nbuf = 2, stages = 0;
     for (; nbuf >= 1; --nbuf) {
       const size_t stg_bytes = (size_t)8 * nbuf * EP_BUF_BYTES;
       stages = fixed + stg_bytes < smem_max ? (int)((smem_max - fixed - stg_bytes) / stage_bytes) : 0;
-      if (stages >= (nbuf_env ? 2 : 3)) break;
+      if (stages >= 3) break;
     }
     if (nbuf < 1) { nbuf = 1; }
-    if (st2_env >= 2 && stages > st2_env) stages = st2_env;
     if (stages >= 2) {
       if (stages > 6) stages = 6;
       EmissionTcParams p2 = p;
@@ -945,7 +933,6 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
       paired = false;
     } else {
       if (stages > 6) stages = 6;
-      if (st_env > 0 && stages > st_env && st_env >= 2) stages = st_env;
       p.stages = stages;
       p.ep_nbuf = nbuf;
       CUtensorMap tmC32, tmC16;
@@ -966,8 +953,7 @@ extern "C" int pmg_emission_poisson_f16(int64_t T, int N, int K, const void* y16
     const uint32_t stage_bytes = TC_A_BYTES + EM_PB * BN * TC_BK * 2;
     int stages = (int)((225 * 1024) / stage_bytes);
     // measured on B200 at the headline shape: 2 stages 1.95 ms, 3 stages 2.08 ms
-    const int cap = st_env > 0 ? st_env : 2;
-    if (stages > cap) stages = cap;
+    if (stages > 2) stages = 2;
     if (stages < 2) return PMG_ERR_UNSUPPORTED_SHAPE;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;

@@ -721,7 +721,6 @@ constexpr int kRegWT = 10;   // compile-time half width of the register-window T
 
 }  // namespace pmg
 #include "pmg_scan_bulk.cuh"
-#include <cstdlib>
 namespace pmg {
 
 static bool bulk_ok(const FwdParams& p) {
@@ -736,35 +735,22 @@ static int bulk_launch(const P& p, int n_groups, cudaStream_t st) {
   if constexpr (FWD) return launch_fwd_bulk<Q, WT, NW, OB>(p, n_groups, st);
   else return launch_bwd_bulk<Q, WT, NW, OB>(p, n_groups, st);
 }
-template <bool FWD, int Q, int WT, typename P>
-static int bulk_variant(const P& p, int n_groups, cudaStream_t st, int var) {
-  switch (var) {
-    case 122: return bulk_launch<FWD, Q, WT, 12, 2>(p, n_groups, st);
-    case 162: return bulk_launch<FWD, Q, WT, 16, 2>(p, n_groups, st);
-    case 161: return bulk_launch<FWD, Q, WT, 16, 1>(p, n_groups, st);
-    default: return bulk_launch<FWD, Q, WT, 8, 2>(p, n_groups, st);
-  }
-}
-
 // choose (Q, WPC): smallest group that covers K with at most 16 bins per thread
 template <bool FWD, typename P>
 static int dispatch(const P& p, int n_groups, cudaStream_t st) {
   const int K = p.c.tr.K;
   const bool reg = p.c.tr.kind == 0 && p.c.tr.W <= kRegWT;
   // whole-row bulk copies need 16-byte rows: K % 8 == 0 (fp16 posterior pieces), ld % 4 == 0
-  static const bool direct_only = std::getenv("PMG_SCAN_DIRECT") != nullptr;
-  // bulk-kernel variant = warps (chains) per CTA * 10 + output staging buffers; tunable for experiments
-  static const int var_fwd = std::getenv("PMG_SCAN_VAR_FWD") ? std::atoi(std::getenv("PMG_SCAN_VAR_FWD")) : 82;
-  static const int var_bwd = std::getenv("PMG_SCAN_VAR_BWD") ? std::atoi(std::getenv("PMG_SCAN_VAR_BWD")) : 82;
-  const int var = FWD ? var_fwd : var_bwd;
+  // bulk kernels: 8 chains per CTA, double-buffered output staging (the best of 8/12/16 chains x 1/2 buffers
+  // measured on B200)
   const bool w5 = p.c.tr.W <= 5;
-  const bool bulk = reg && !direct_only && (K % 8 == 0) && (p.c.ldll % 4 == 0) && bulk_ok(p) && p.c.scale > 0.f;
+  const bool bulk = reg && (K % 8 == 0) && (p.c.ldll % 4 == 0) && bulk_ok(p) && p.c.scale > 0.f;
 #define PMG_CASE(Qv, WPCv)                                                                     \
   do {                                                                                         \
     if (bulk && WPCv == 1) {                                                                   \
       int rc_;                                                                                 \
-      if (w5) rc_ = bulk_variant<FWD, Qv, 5>(p, n_groups, st, var);                           \
-      else rc_ = bulk_variant<FWD, Qv, 10>(p, n_groups, st, var);                              \
+      if (w5) rc_ = bulk_launch<FWD, Qv, 5, 8, 2>(p, n_groups, st);                           \
+      else rc_ = bulk_launch<FWD, Qv, 10, 8, 2>(p, n_groups, st);                              \
       if (rc_ != PMG_ERR_UNSUPPORTED_SHAPE) return rc_;                                        \
     }                                                                                          \
     if (reg) {                                                                                 \

@@ -109,6 +109,12 @@ class EStep:
         # tier 1 of the seam repair (conditional relaunch on the device); off = every repair is a host sweep
         self.device_repair = os.environ.get("PMG_DEVICE_REPAIR", "1") != "0"
         self.halo_min = min(self.halo, DEFAULT_HALO_MIN)     # raised below once the chunk length is known
+        self.dense = getattr(op, "dense", None)      # lockstep tensor-core scan (dense / wide-band move kernels)
+        if chunk_len is None and self.dense is not None and self.halo > 0:
+            # one wave of 128-chain accumulator tiles; a pass costs (warm-up + chunk) GEMM steps
+            mc = min(MIN_CHUNK, 2 * self.halo) if self.adaptive else 2 * self.halo
+            target = self.dense.chains(self.sm_count)
+            chunk_len = min(self.T_core, max(mc, (self.T_core + target - 1) // target))
         if chunk_len is None:
             wide = em_mode and self.compact_ok and self.K > 31 * 8       # the 12-chain variants exist for K > 248
             chunk_len = plan_chunks(self.T_core, self.halo, self.sm_count, EM_CHAINS_PER_SM if wide else 8,
@@ -437,7 +443,7 @@ class EStep:
         self.halos = [nxt, new]
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
-            before_sync=None, forward_only=False, graph_ok=False):
+            before_sync=None, forward_only=False, graph_ok=False, want_tw=None):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
         the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes, the
         device repairs and the seam checks are enqueued, before the launching thread waits for the verdict (work
@@ -446,12 +452,17 @@ class EStep:
         i.e. whether what it read from this E-step's outputs was final).
         forward_only: emission + filter only (log marginal, one-step predictive marginals): what the batched callers
         of the reference (model selection, shuffle tests) read from decode_latent.
+        want_tw: per-chain sums of the latent posterior (``res.tw``; general kernels only).  Default: only when no
+        ``gamma16`` is requested -- with the fp16 pieces the statistics GEMM returns sum_t gamma through the column
+        of ones of the counts.
         graph_ok: the caller vouches that ``tuning``, ``gamma16`` and everything ``before_sync`` touches are fixed
         buffers and that ``before_sync`` only enqueues GPU work (no Python state): the launch sequence may then be
         captured into a CUDA graph and replayed."""
         S, K = self.S, self.K
         if forward_only:
             want_gamma = want_gamma_lat = want_dyn = want_r = False
+        if want_tw is None:
+            want_tw = gamma16 is None
         f32 = dict(dtype=torch.float32, device=self.dev)
         # EM fast path: only the fp16 posterior pieces and sum_t gamma are wanted -> compact kernels
         compact = (self.compact_ok and (gamma16 is not None or forward_only)
@@ -474,6 +485,9 @@ class EStep:
         tol = self.seam_tol
         hf = (self.hf[self.h_cur], self.hf[1 - self.h_cur]) if self.adaptive else (None, None)
         hb = (self.hb[self.h_cur], self.hb[1 - self.h_cur]) if self.adaptive else (None, None)
+        # longest warm-up of this pass (the lockstep scan runs that many + chunk_len steps)
+        hmax_f = int(self.hf_host[self.h_cur].max()) if (self.adaptive and self.dense is not None) else 0
+        hmax_b = int(self.hb_host[self.h_cur].max()) if (self.adaptive and self.dense is not None) else 0
 
         def fwd(mode=0, ids=None):
             sel = dict(sel_err=err_f, sel_tol=tol) if mode == 2 else {}
@@ -486,7 +500,8 @@ class EStep:
                 return
             ops.forward(self.plan, self.op, self.ll, self.alpha, self.lmr, carry_in=self.carry_in,
                         halo_state=(self.halo_state if mode == 0 else None), mode=mode, chain_ids=ids,
-                        warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt], **sel)
+                        warm_in=(f_in if mode == 0 else self.halo_state), warm_out=self.fwarm[nxt],
+                        halo_max=hmax_f, **sel)
 
         def bwd(mode=0, ids=None):
             sel = dict(sel_err=err_b, sel_tol=tol) if mode == 2 else {}
@@ -497,9 +512,10 @@ class EStep:
                                      warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out, **sel)
                 return
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
-                         r_out=r, tw_partial=self.tw_partial, beta_halo=self.beta_halo, beta_end=self.beta_end,
+                         r_out=r, tw_partial=(self.tw_partial if want_tw else None), beta_halo=self.beta_halo,
+                         beta_end=self.beta_end,
                          mode=mode, chain_ids=ids, gamma16=gamma16,
-                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out, **sel)
+                         warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out, halo_max=hmax_b, **sel)
 
         seams = S > 1 or self.shard.active
         lmr = self.ax[:, K + 1] if compact else self.lmr
@@ -618,7 +634,8 @@ class EStep:
         res.r = r[c] if r is not None else None
         # local sums; the caller all-reduces them together with the spike-weighted statistics
         # (the compact path leaves sum_t gamma to the statistics GEMM: ones column of the fp16 counts)
-        res.tw = None if (compact or forward_only) else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32)
+        res.tw = (None if (compact or forward_only or not want_tw)
+                  else self.tw_partial.sum(dim=0, dtype=torch.float64).to(torch.float32))
         # global (summed over ranks) log marginal: a host scalar, it came with the verdict
         res.log_marginal = self.tail_host[T_LML].clone()
         res.n_relay_fwd, res.n_relay_bwd = n_relay_f, n_relay_b

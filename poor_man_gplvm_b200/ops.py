@@ -119,8 +119,7 @@ class CountsF16:
         _f32(y, "y", 2)
         self.T, self.N = y.shape
         self.ones_col = bool(ones_col)
-        al = int(os.environ.get("PMG_Y16_ALIGN", "8"))              # experiment: 64 = 128-byte aligned rows
-        self.ld = (self.N + (1 if ones_col else 0) + al - 1) // al * al
+        self.ld = (self.N + (1 if ones_col else 0) + 7) // 8 * 8   # 16-byte rows (TMA); wider padding did not pay
         self.data = torch.empty((self.T, self.ld), dtype=torch.float16, device=y.device)
         self._inexact = torch.zeros(1, dtype=torch.int32, device=y.device)
         self.lgam = self.ysum = None
@@ -356,13 +355,62 @@ def stationary_joint(P0, M):
     return (pi / pi.sum()).astype(np.float32)
 
 
+def dense_scan_pays(K, W):
+    """The lockstep tensor-core scan costs ~3 K^2 tensor flops per bin and pass, a band kernel K (2W+1) CUDA-core
+    flops: the GEMM form wins once the band covers a good part of the matrix."""
+    return K >= 256 and (2 * W + 1) * 4 >= K
+
+
+class DenseMoveTC:
+    """Right-hand operands of the lockstep scan GEMMs: the row-normalised move matrix P0 scaled by 2^14 as two fp16
+    pieces, once transposed (forward pass: D[c,x'] = sum_x u[c,x] P0[x,x']) and once as is (backward pass), plus
+    the 64-column block range every column tile touches (band structure)."""
+    SCALE = 16384.0
+
+    def __init__(self, P0, device):
+        lib = _lib.load()
+        P0 = np.asarray(P0, dtype=np.float64)
+        K = P0.shape[0]
+        geo = [C.c_int(0) for _ in range(4)]
+        check(lib.pmg_dense_scan_geometry(K, *[C.byref(g) for g in geo]), "pmg_dense_scan_geometry")
+        self.K, (self.Kk, self.Kn, self.BN, self.n_ntiles) = K, [g.value for g in geo]
+        buf = np.zeros((2, 2, self.Kn, self.Kk), dtype=np.float16)
+        rng = np.zeros((2, self.n_ntiles, 2), dtype=np.int32)
+        for d, B in enumerate((P0.T, P0)):
+            sc = B * self.SCALE
+            hi = sc.astype(np.float16)
+            lo = (sc - hi.astype(np.float64)).astype(np.float16)
+            buf[d, 0, :K, :K] = hi
+            buf[d, 1, :K, :K] = lo
+            nz = (buf[d, 0] != 0) | (buf[d, 1] != 0)
+            for i in range(self.n_ntiles):
+                cols = np.nonzero(nz[i * self.BN:(i + 1) * self.BN].any(axis=0))[0]
+                rng[d, i] = (cols.min() // 64, cols.max() // 64 + 1) if cols.size else (0, 1)
+        self.P16 = torch.from_numpy(buf).to(device)
+        self.kb_host = np.ascontiguousarray(rng)
+        self.kb_ptr = self.kb_host.ctypes.data_as(C.POINTER(C.c_int))
+        self._ws = {}
+
+    def workspace(self, n_chain, device):
+        ws = self._ws.get(n_chain)
+        if ws is None:
+            nbytes = int(_lib.load().pmg_dense_scan_workspace_bytes(int(n_chain), self.K))
+            ws = self._ws[n_chain] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return ws
+
+    def chains(self, sm_count):
+        """chains that fill the GPU with one wave of 128-chain x BN-column accumulator tiles"""
+        return 128 * max(1, sm_count // self.n_ntiles)
+
+
 class MoveOperator:
     """Device copy of the factored "move" transition + the 2x2 dynamics matrix."""
 
-    def __init__(self, host, M, device, P0=None):
+    def __init__(self, host, M, device, P0=None, dense_tc=None):
         """P0: optional dense row-normalised move matrix [K,K] (host); when given, the stationary
         distribution of the joint (dynamics x latent) prior chain is computed and used as the
-        message that time-parallel warm-ups start from."""
+        message that time-parallel warm-ups start from.
+        dense_tc: run mode-0 passes as lockstep tensor-core GEMMs (None = when the band is wide enough to pay)."""
         self.K = int(host["inv_z"].shape[0]) if host["kind"] == 0 else int(host["band_fwd"].shape[1])
         self.kind, self.W = int(host["kind"]), int(host["W"])
         self.M = np.asarray(M, dtype=np.float32).reshape(4)
@@ -374,6 +422,14 @@ class MoveOperator:
         self.stationary = None
         if P0 is not None:
             self.stationary = dev(stationary_joint(np.asarray(P0, dtype=np.float64), self.M.reshape(2, 2)))
+        # dense / wide-band kernels: lockstep tensor-core scan (pmg_forward_dense / pmg_backward_dense)
+        self.dense = None
+        if dense_tc is None:
+            dense_tc = P0 is not None and dense_scan_pays(self.K, self.W)
+        if dense_tc:
+            if P0 is None:
+                raise ValueError("the tensor-core scan needs the dense row-normalised move matrix P0")
+            self.dense = DenseMoveTC(P0, device)
 
     def cstruct(self):
         """ctypes view of the operator (built once: the device arrays never move)"""
@@ -432,12 +488,21 @@ def _warm(warm_in):
 
 
 def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None, warm_in=None,
-            warm_out=None, sel_err=None, sel_tol=0.0):
+            warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0):
+    """halo_max: upper bound of the per-chain warm-ups set with set_chain_halos (lockstep scan only)."""
     lib = _lib.load()
     _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
+    dense = getattr(op, "dense", None)
+    if mode == 0 and dense is not None:
+        wk = dense.workspace(plan.n_chain, ll.device)
+        check(lib.pmg_forward_dense(C.byref(plan), C.byref(tr), _p(dense.P16), dense.kb_ptr, int(halo_max), _p(ll),
+                                    ll.shape[1], _p(carry_in), wp, ws, _p(warm_out), _p(alpha), _p(lmr),
+                                    _p(halo_state), _p(wk), wk.numel(), _stream()), "pmg_forward_dense")
+        _count(2 * (max(plan.halo, int(halo_max)) + plan.chunk_len) + 1)
+        return
     check(lib.pmg_forward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(carry_in), wp, ws, _p(warm_out),
                           _p(alpha), _p(lmr),
                           _p(halo_state), int(mode), _p(chain_ids), n_ids, _stream()), "pmg_forward")
@@ -446,12 +511,22 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
              beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
-             warm_out=None, sel_err=None, sel_tol=0.0):
+             warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0):
     lib = _lib.load()
     _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
+    dense = getattr(op, "dense", None)
+    if mode == 0 and dense is not None:
+        wk = dense.workspace(plan.n_chain, ll.device)
+        check(lib.pmg_backward_dense(C.byref(plan), C.byref(tr), _p(dense.P16), dense.kb_ptr, int(halo_max), _p(ll),
+                                     ll.shape[1], _p(alpha), _p(beta_in), wp, ws, _p(warm_out), _p(gamma),
+                                     _p(gamma_lat), _p(gamma16), (gamma16.shape[2] if gamma16 is not None else 0),
+                                     _p(dyn_marg), _p(r_out), _p(tw_partial), _p(beta_halo), _p(beta_end), _p(wk),
+                                     wk.numel(), _stream()), "pmg_backward_dense")
+        _count(2 * (max(plan.halo, int(halo_max)) + plan.chunk_len))
+        return
     check(lib.pmg_backward(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(alpha), _p(beta_in), wp, ws,
                            _p(warm_out), _p(gamma),
                            _p(gamma_lat), _p(gamma16), (gamma16.shape[2] if gamma16 is not None else 0), _p(dyn_marg),

@@ -64,7 +64,7 @@ def _halo_own(plan, s):
 
 
 def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, chain_ids=None, warm_in=None,
-            warm_out=None, sel_err=None, sel_tol=0.0):
+            warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0):
     K = op.K
     P0 = _dense_move(op)
     M = op.M.reshape(2, 2).astype(np.float64)
@@ -114,7 +114,7 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
              beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
-             warm_out=None, sel_err=None, sel_tol=0.0):
+             warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0):
     K, T = op.K, int(plan.T)
     P0 = _dense_move(op)
     M = op.M.reshape(2, 2).astype(np.float64)

@@ -179,6 +179,69 @@ def test_forward_backward_matches_linear_oracle(ops, K, mv, custom, T, chunk_len
     assert np.max(np.abs(xi - want["xi"])) < 2e-4 * max(1.0, want["xi"].max())
 
 
+DENSE_TC_CASES = [
+    # K, kernel, T, chunk_len, halo      -> (column tiles, K blocks) of the lockstep GEMM
+    (256, "dense", 1500, 125, 96),       # 1 column tile, 4 K blocks, 12 chains
+    (400, "wide", 900, 100, 80),         # 2 column tiles of 208, Kk = 448; Toeplitz kernel with a wide band
+    (520, "dense", 700, 64, 64),         # 3 column tiles
+    (320, "band", 800, 200, 128),        # block-banded custom kernel: K-block ranges skip the zero blocks
+    (256, "dense", 300, 300, 0),         # one exact chain
+]
+
+
+@pytest.mark.parametrize("K,kernel,T,chunk_len,halo", DENSE_TC_CASES)
+def test_lockstep_tensor_core_scan_matches_linear_oracle(ops, K, kernel, T, chunk_len, halo):
+    """pmg_forward_dense / pmg_backward_dense (dense and wide-band move kernels as one tcgen05 GEMM per time step
+    over all chains, reference decoder.py:151-256 with gp_kernel.py:61-66 kernels) against the fp64 oracle, and
+    against the CUDA-core general path on the same inputs."""
+    from poor_man_gplvm_b200.estep import EStep
+    rng = np.random.default_rng(K + T)
+    N = 20
+    d = make_dataset(T, N, K, seed=K + 1)
+    x = np.arange(K)
+    dist = np.abs(x[:, None] - x[None, :])
+    ck, mv = None, 1.0
+    if kernel == "dense":
+        ck = np.exp(-dist / 40.0) * (1 + 0.3 * rng.random((K, K))) + 0.01
+    elif kernel == "band":
+        ck = np.exp(-dist / 30.0) * (dist <= 70) * (1 + 0.3 * rng.random((K, K)))
+    else:
+        mv = 25.0
+    P, logP, M, logM, hostop = _transition(K, mv, ck)
+    ma_l = np.ones(K); ma_l[K // 3] = 0
+    ll = lin.emission_gemm_form(d["y"], d["tuning_true"], np.ones(N), ma_l).astype(np.float32)
+    scale = 0.9
+    want = lin.e_step(d["y"], d["tuning_true"], P.astype(np.float64), M.astype(np.float64), np.ones(N), ma_l,
+                      likelihood_scale=scale, want_xi=True)
+    outs = {}
+    for tc in (True, False):
+        op = ops.MoveOperator(hostop, M, torch.device("cuda"), P0=P[0], dense_tc=tc)
+        assert (op.dense is not None) == tc
+        es = EStep(torch.zeros((T, 1), device="cuda"), op, None, None, scale, halo=halo, chunk_len=chunk_len)
+        es.ll.copy_(dev(ll))
+        es.emission = lambda tuning, es=es: es.ll
+        g16 = ops.new_gamma16(T, K, torch.device("cuda"))
+        res = es.run(None, want_gamma=True, want_gamma_lat=True, want_dyn=True, want_r=True, gamma16=g16, want_tw=True)
+        outs[tc] = res
+        assert res.n_relay_fwd == 0 and res.n_relay_bwd == 0
+        assert np.max(np.abs(host(res.alpha) - want["alpha"])) < 1e-5
+        assert np.max(np.abs(host(res.gamma) - want["gamma"])) < 1e-5
+        assert np.max(np.abs(host(res.gamma_lat) - want["gamma"].sum(axis=1))) < 1e-5
+        assert np.max(np.abs(host(res.dyn_marg) - want["gamma"].sum(axis=2))) < 1e-5
+        assert abs(float(res.log_marginal) - want["log_marginal"]) < 1e-4 * abs(want["log_marginal"])
+        assert np.max(np.abs(host(res.lmr) - want["lmr"])) < 1e-3
+        assert np.max(np.abs(host(res.tw) - want["gamma"].sum(axis=(0, 1)))) < 1e-3
+        pieces = host(g16.float())
+        assert np.max(np.abs(pieces[0, :, :K] + pieces[1, :, :K] - want["gamma"].sum(axis=1))) < 1e-5
+        G = ops.atb(res.alpha.view(T, 2 * K)[:T - 1], res.r.view(T, 2 * K)[1:])
+        xi = np.exp(host(ops.xi_finalize(G, dev(logP), logM)).astype(np.float64))
+        assert abs(xi.sum() - (T - 1)) < 1e-3 * (T - 1)
+        assert np.max(np.abs(xi - want["xi"])) < 2e-4 * max(1.0, want["xi"].max())
+    # the two paths agree far inside the tolerance (22-bit operand pieces vs fp32)
+    assert np.max(np.abs(host(outs[True].gamma) - host(outs[False].gamma))) < 5e-6
+    assert abs(float(outs[True].log_marginal) - float(outs[False].log_marginal)) < 2e-6 * abs(want["log_marginal"])
+
+
 def test_relay_repairs_failed_seams(ops):
     """With a useless halo every seam fails; the relay must reproduce the sequential answer."""
     K, T, N = 100, 600, 15

@@ -141,8 +141,18 @@ def test_session_shape_default_adam():
     want = lin.fit_em_linear(oracle, d["y"], m_step_schedule=[int(n) for n in n_got], **kw)
     lw = np.array(want["log_marginal_l"])
     assert np.max(np.abs(lg - lw) / np.abs(lw)) < 1e-4, (lg, lw)
-    assert np.max(np.abs(got["tuning"] - want["tuning"]) / want["tuning"]) < 1e-3
-    assert np.max(np.abs(got["posterior_latent_marg"] - want["posterior_latent_marg"])) < 5e-5
+    t_err = np.max(np.abs(got["tuning"] - want["tuning"]) / want["tuning"])
+    assert t_err < 1e-3
+    # final posterior: against the fp64 E-step evaluated at the tuning the CUDA path arrived at (the E-step is exact;
+    # hundreds of fp32 Adam steps leave the tuning within its 1e-3, and with 200 neurons the posterior amplifies
+    # that difference), plus the sensitivity bound against the oracle's own chain -- as in the headline-shape test
+    P, _, M, _ = oracle._transitions({})
+    es = lin.e_step(d["y"].astype(np.float64), got["tuning"].astype(np.float64), P.astype(np.float64),
+                    M.astype(np.float64), oracle.ma_neuron_default, oracle.ma_latent_default)
+    tol = _post_tol(es["ll"])
+    assert np.max(np.abs(got["posterior_latent_marg"] - es["gamma"].sum(axis=1))) < tol
+    assert np.max(np.abs(got["posterior_dynamics_marg"] - es["gamma"].sum(axis=2))) < tol
+    assert np.max(np.abs(got["posterior_latent_marg"] - want["posterior_latent_marg"])) < max(5e-5, 50 * t_err)
 
 
 def test_naive_bayes_config_c_shape():

@@ -239,3 +239,30 @@ def test_circular_shuffle_and_latent_masks_on_host():
     e = shuf.compute_entropy(np.log(np.full((3, 2, 4), 1 / 8)))
     assert np.allclose(e, np.log(8))
     assert shuf.compute_entropy(np.array([[0.0, -np.inf]]), axis=-1)[0] == 0.0
+
+
+def test_dense_scan_operand_pack_cpu():
+    """Right-hand operands of the lockstep tensor-core scan (host-side packing, no GPU needed): the two fp16 pieces
+    reconstruct 2^14 * P0 to 22 bits, the forward operand is the transpose of the backward one, padding is zero and
+    the K-block ranges cover every non-zero of a block-banded kernel and skip the blocks outside the band."""
+    from poor_man_gplvm_b200 import ops
+    K = 300
+    x = np.arange(K)
+    dist = np.abs(x[:, None] - x[None, :])
+    P0 = np.exp(-dist / 9.0) * (dist <= 40)
+    P0 = P0 / P0.sum(axis=1, keepdims=True)
+    d = ops.DenseMoveTC(P0, "cpu")
+    assert (d.Kk, d.Kn, d.BN, d.n_ntiles) == (320, 320, 160, 2)
+    buf = d.P16.numpy().astype(np.float64)
+    rec = (buf[:, 0] + buf[:, 1]) / d.SCALE
+    assert np.max(np.abs(rec[1, :K, :K] - P0)) <= 2.0 ** -22 * P0.max() * 1.01
+    assert np.array_equal(buf[0, :, :K, :K], np.swapaxes(buf[1, :, :K, :K], 1, 2))
+    assert not buf[:, :, K:].any() and not buf[:, :, :, K:].any()
+    for dd in range(2):
+        for i in range(d.n_ntiles):
+            lo, hi = d.kb_host[dd, i]
+            rows = rec[dd, i * d.BN:(i + 1) * d.BN]
+            assert not rows[:, :lo * 64].any() and not rows[:, hi * 64:].any()
+            assert rows[:, lo * 64:(lo + 1) * 64].any() and rows[:, (hi - 1) * 64:hi * 64].any()
+    assert tuple(d.kb_host[0, 0]) == (0, 4) and tuple(d.kb_host[0, 1]) == (1, 5)
+    assert ops.dense_scan_pays(2000, 1999) and not ops.dense_scan_pays(400, 5) and not ops.dense_scan_pays(100, 99)
