@@ -173,6 +173,22 @@ int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const floa
                  void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo, float* beta_end,
                  int mode, const int* chain_ids, int n_ids, pmg_stream_t stream);
 
+/* pmg_backward that writes the operands of the transition-count GEMM (decoder.py:215-221) directly as
+ * bf16 hi/lo pieces instead of the fp32 r_out -- no separate pmg_split_bf16 passes over two [T,2K] arrays:
+ *   row t   of xa_hi / xa_lo [T, ld_x] = alpha_t [2K]           (hi = bf16(v), lo = bf16(v - hi))
+ *   row t+1 of xr_hi / xr_lo [T, ld_x] = r_{t+1} / z_t [2K]
+ * for the core bins t (rows nobody writes are left untouched).  ld_x >= 2K, ld_x % 8 == 0, 16-byte aligned pointers.
+ * Supported where pmg_backward runs its bulk kernel (pmg_backward_xi16_supported: Toeplitz kernel with W <= 10,
+ * K % 8 == 0, K <= 512, likelihood_scale > 0); PMG_ERR_UNSUPPORTED_SHAPE otherwise.  Feed the pieces to
+ * pmg_atb_bf16x2_pieces. */
+int pmg_backward_xi16_supported(const pmg_transition* tr, float likelihood_scale);
+int pmg_backward_xi16(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                      const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
+                      float* warm_out, float* gamma, float* gamma_lat, void* gamma16, int64_t ldg, float* dyn_marg,
+                      void* xa_hi, void* xa_lo, void* xr_hi, void* xr_lo, int64_t ld_x, float* tw_partial,
+                      float* beta_halo, float* beta_end, int mode, const int* chain_ids, int n_ids,
+                      pmg_stream_t stream);
+
 /* err[i] = max relative difference between est[i,:]/sum(est[i,:]) and truth[i,:]/sum(truth[i,:]) over entries
  * whose normalised value is > floor (messages are defined up to a positive scale: every step of both passes
  * renormalises).  est/truth are [n, len] with row strides in elements (truth rows may live inside alpha). */
@@ -229,6 +245,20 @@ int pmg_backward_dense(const pmg_scan_plan* plan, const pmg_transition* tr, cons
                        float* beta_halo, float* beta_end, void* workspace, int64_t workspace_bytes,
                        pmg_stream_t stream);
 
+/* Boundary messages of a time-sharded forward pass (the reference is single-device), one small kernel
+ * on each side of the exchange instead of ~20 tensor ops.  out [8K] = [to_left: first (2K) | unused (2K) |
+ * to_right: last (2K) | warm (2K)] with `warm` = this pass's message at the bin in front of the right neighbour's next
+ * warm-up: warm_mode 0 zeros, 1 = warm_src [2K], 2 = built from a compact row (ax_row [K+4], ll_row [K]).
+ * unpack: from_left [4K] (the left rank's to_right) -> fwd_end0 [2K] (seam truth), fwarm0 [2K] (warm start, may be
+ * NULL); from_right [4K] (the right rank's to_left) -> the row behind this block: alpha_stop [2K], or with compact != 0
+ * ax_stop [K+4] (alpha[0,:] and the scalar a1s for ll_stop [K]).  NULL inputs are skipped. */
+int pmg_boundary_pack_fwd(int K, const float* first, const float* last, int warm_mode, const float* warm_src,
+                          const float* ax_row, const float* ll_row, float likelihood_scale, float* out,
+                          pmg_stream_t stream);
+int pmg_boundary_unpack_fwd(int K, const float* from_left, const float* from_right, float* fwd_end0, float* fwarm0,
+                            int compact, float* ax_stop, const float* ll_stop, float likelihood_scale,
+                            float* alpha_stop, pmg_stream_t stream);
+
 /* dst[0] = sum_{i<n} src[i*stride], accumulated in fp64 in a fixed order (the log marginal of a pass is the sum of the
  * one-step predictive log marginals, decoder.py:170,186).  workspace: pmg_strided_sum_workspace_bytes() bytes,
  * 8-byte aligned, zeroed ONCE by the caller (the kernel re-arms it); one call at a time per workspace. */
@@ -264,6 +294,12 @@ int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg, const voi
 int pmg_split_bf16(int64_t T, int K, const float* src, int64_t lds, void* dst16, int64_t ld16, pmg_stream_t stream);
 int pmg_atb_bf16x2(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
                    float* out, void* workspace, int64_t workspace_bytes, pmg_stream_t stream);
+
+/* pmg_atb_bf16x2 with every piece behind its own pointer (T rows each; ldg / ldy16 per operand): the pieces written
+ * by pmg_backward_xi16 are used in place, at a row offset (alpha rows [t0, t1) against r rows [t0+1, t1+1)). */
+int pmg_atb_bf16x2_pieces(int64_t T, int K, int N, const void* g_hi, const void* g_lo, int64_t ldg,
+                          const void* y_hi, const void* y_lo, int64_t ldy16, float* out, void* workspace,
+                          int64_t workspace_bytes, pmg_stream_t stream);
 
 /* log_acc[d,d',x,x'] = logM[d,d'] + logP_{d'}[x,x'] + log G[(d,x),(d',x')]   (G = alpha^T r, [2K,2K]):
  * decoder.py:221's accumulator; using the analytic log kernel keeps deep tails finite.

@@ -73,6 +73,17 @@ SIGNATURES = {
                                      C.c_int, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p,
                                      c_f32p, C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                      C.c_void_p, C.c_int64, c_stream]),
+    "pmg_backward_xi16_supported": (C.c_int, [C.POINTER(PmgTransition), C.c_float]),
+    "pmg_backward_xi16": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
+                                    c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int64, c_f32p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p,
+                                    C.c_int, c_i32p, C.c_int, c_stream]),
+    "pmg_atb_bf16x2_pieces": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_void_p, C.c_int64, c_f32p, C.c_void_p, C.c_int64, c_stream]),
+    "pmg_boundary_pack_fwd": (C.c_int, [C.c_int, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_float, c_f32p,
+                                        c_stream]),
+    "pmg_boundary_unpack_fwd": (C.c_int, [C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, C.c_float,
+                                          c_f32p, c_stream]),
     "pmg_scan_compact_supported": (C.c_int, [C.POINTER(PmgTransition), C.c_float]),
     "pmg_forward_compact": (C.c_int, [C.POINTER(PmgScanPlan), C.POINTER(PmgTransition), c_f32p, C.c_int64, c_f32p,
                                       c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int,

@@ -471,7 +471,10 @@ class PoissonGPLVMJump1D:
         K = self.n_latent_bin
         c = res.core
         hi = c.stop - 1 if es.shard.is_last else c.stop          # pairs (t, t+1) with t in [c.start, hi)
-        if hi > c.start:
+        if hi > c.start and res.xi16 is not None:
+            # the backward pass wrote both operands as bf16 hi/lo pieces: tensor cores, three products
+            G = ops.atb_bf16x2_pieces(res.xi16, c.start, hi - c.start)
+        elif hi > c.start:
             A = res.alpha_ext.view(-1, 2 * K)[c.start:hi]
             R = res.r_ext.view(-1, 2 * K)[c.start + 1:hi + 1]
             # long recordings: tensor cores on bf16 hi/lo pieces (three products); short ones: fp32 CUDA cores
@@ -495,7 +498,8 @@ class PoissonGPLVMJump1D:
         P, logP, M, logM, op = self._transition_pack(hyperparam)
         ma_n, ma_l = self._masks(ma_neuron, ma_latent, y_dev.shape[0])
         es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, emission_factory=self._emission_factory(hyperparam))
-        res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=False, want_dyn=False, want_r=_want_r)
+        res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=False, want_dyn=False, want_r=_want_r,
+                     xi16_ok=y_dev.shape[0] - 1 >= ops.XI_TC_MIN_BINS)
         log_acc = None
         if _want_r and y_dev.shape[0] > 1:
             log_acc = self._transition_counts(es, res, logP, logM)
@@ -523,7 +527,7 @@ class PoissonGPLVMJump1D:
         es = EStep(y_dev, op, ma_n, ma_l, likelihood_scale, shard=TimeShard(group) if time_sharded else None,
                    emission_factory=self._emission_factory(hyperparam))
         res = es.run(self._dev(tuning), want_gamma=True, want_gamma_lat=True, want_dyn=True,
-                     want_r=(T > 1 or es.shard.active))
+                     want_r=(T > 1 or es.shard.active), xi16_ok=T - 1 >= ops.XI_TC_MIN_BINS)
         conv = (lambda t: t) if return_device else self._host
         # the reference leaves these on the device as jax arrays (core.py:489, decoder.py:360-375)
         lazy = (lambda t: t) if return_device else hostio.LazyHostArray

@@ -977,6 +977,7 @@ constexpr int AT_PG = 2;                         // fp16 pieces of gamma
 
 struct AtbTcParams {
   int64_t T, t_per_split;
+  int64_t g_lo_row;  // row of the lo piece's first time bin in its tensor map (T: pieces stacked in one matrix; 0: own map)
   int K, N, BN, n_mtiles, n_ntiles, splits, stages;
   uint32_t tmem_cols;
   float* partial;    // [splits][K][N]
@@ -990,7 +991,8 @@ struct AtbTcParams {
 template <int PA, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY1,
-              const __grid_constant__ CUtensorMap tmG, const AtbTcParams p) {
+              const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG1,
+              const AtbTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int mp = blockIdx.x, nt = blockIdx.y, sp = blockIdx.z;
@@ -1015,7 +1017,7 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmG); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmG1); }
   if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -1048,8 +1050,8 @@ atb_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         }
         for (int pc = 0; pc < AT_PG; ++pc)
           for (int b = 0; b < n_boxes_b; ++b)
-            tma_load_2d(sA + a_bytes + pc * b_piece_bytes + b * AT_BOX_BYTES, &tmG, &full[stage], k_base + b * 64,
-                        (int)(pc * p.T) + t0);
+            tma_load_2d(sA + a_bytes + pc * b_piece_bytes + b * AT_BOX_BYTES, pc == 0 ? &tmG : &tmG1, &full[stage],
+                        k_base + b * 64, (int)(pc * p.g_lo_row) + t0);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -1241,13 +1243,13 @@ extern "C" int pmg_split_bf16(int64_t T, int K, const float* src, int64_t lds, v
   return PMG_OK;
 }
 
-static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16,
-                             const void* y16_lo, int64_t ldy16, int fmt, float* yw, void* workspace,
+static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, const void* g16_lo, int64_t ldg,
+                             const void* y16, const void* y16_lo, int64_t ldy16, int fmt, float* yw, void* workspace,
                              int64_t workspace_bytes, pmg_stream_t stream);
 
 extern "C" int pmg_atb_f16(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16, int64_t ldy16,
                            float* yw, void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
-  return atb_pieces_launch(T, K, N, g16, ldg, y16, nullptr, ldy16, 0, yw, workspace, workspace_bytes, stream);
+  return atb_pieces_launch(T, K, N, g16, nullptr, ldg, y16, nullptr, ldy16, 0, yw, workspace, workspace_bytes, stream);
 }
 
 // out[k,n] = sum_t G[t,k] * Y[t,n] with BOTH operands given as two bf16 pieces ([2][T][ld], hi then lo):
@@ -1257,16 +1259,25 @@ extern "C" int pmg_atb_bf16x2(int64_t T, int K, int N, const void* g16, int64_t 
                               float* out, void* workspace, int64_t workspace_bytes, pmg_stream_t stream) {
   if (!y16 || T <= 0) return PMG_ERR_BAD_ARG;
   const char* lo = (const char*)y16 + (size_t)T * (size_t)ldy16 * 2;
-  return atb_pieces_launch(T, K, N, g16, ldg, y16, lo, ldy16, 1, out, workspace, workspace_bytes, stream);
+  return atb_pieces_launch(T, K, N, g16, nullptr, ldg, y16, lo, ldy16, 1, out, workspace, workspace_bytes, stream);
 }
 
-static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, int64_t ldg, const void* y16,
-                             const void* y16_lo, int64_t ldy16, int fmt, float* yw, void* workspace,
+// Same product with every piece behind its own pointer (rows of T bins, common leading dimension per operand): the
+// pieces the backward scan writes for the transition counts (pmg_backward_xi16) are used in place, at a row offset.
+extern "C" int pmg_atb_bf16x2_pieces(int64_t T, int K, int N, const void* g_hi, const void* g_lo, int64_t ldg,
+                                     const void* y_hi, const void* y_lo, int64_t ldy16, float* out, void* workspace,
+                                     int64_t workspace_bytes, pmg_stream_t stream) {
+  if (!g_hi || !g_lo || !y_hi || !y_lo || T <= 0) return PMG_ERR_BAD_ARG;
+  return atb_pieces_launch(T, K, N, g_hi, g_lo, ldg, y_hi, y_lo, ldy16, 1, out, workspace, workspace_bytes, stream);
+}
+
+static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, const void* g16_lo, int64_t ldg,
+                             const void* y16, const void* y16_lo, int64_t ldy16, int fmt, float* yw, void* workspace,
                              int64_t workspace_bytes, pmg_stream_t stream) {
   using namespace pmg;
   if (T <= 0 || K <= 0 || N <= 0 || !g16 || !y16 || !yw) return PMG_ERR_BAD_ARG;
   if (ldg < K || (ldg & 7) || ldy16 < N || (ldy16 & 7)) return PMG_ERR_BAD_ARG;
-  if (((uintptr_t)g16 & 15) || ((uintptr_t)y16 & 15)) return PMG_ERR_ALIGNMENT;
+  if (((uintptr_t)g16 & 15) || ((uintptr_t)y16 & 15) || ((uintptr_t)g16_lo & 15)) return PMG_ERR_ALIGNMENT;
   if ((int64_t)AT_PG * T > ((int64_t)1 << 31) - 256) return PMG_ERR_UNSUPPORTED_SHAPE;
   AtbTcParams p;
   atb_tc_plan(T, K, N, p.BN, p.n_mtiles, p.n_ntiles, p.splits, p.t_per_split);
@@ -1281,24 +1292,32 @@ static int atb_pieces_launch(int64_t T, int K, int N, const void* g16, int64_t l
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.BN);
 
-  CUtensorMap tmY, tmY1, tmG;
+  CUtensorMap tmY, tmY1, tmG, tmG1;
   // inner (contiguous) dimension = neurons / latent bins, outer = time; box = 32 time rows x 64 columns
   // (fp16 and bf16 share the 2-byte tensor-map geometry; the data type only matters to the MMA descriptor)
   int rc = make_tmap_f16(&tmY, y16, (uint64_t)T, (uint64_t)ldy16, (uint64_t)ldy16, AT_BKT);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
   rc = make_tmap_f16(&tmY1, y16_lo ? y16_lo : y16, (uint64_t)T, (uint64_t)ldy16, (uint64_t)ldy16, AT_BKT);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
-  rc = make_tmap_f16(&tmG, g16, (uint64_t)AT_PG * T, (uint64_t)ldg, (uint64_t)ldg, AT_BKT);
+  // posterior-side pieces: stacked [2][T][ldg] in one matrix (lo piece T rows further down), or one matrix each
+  rc = make_tmap_f16(&tmG, g16, (uint64_t)(g16_lo ? 1 : AT_PG) * T, (uint64_t)ldg, (uint64_t)ldg, AT_BKT);
   if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+  tmG1 = tmG;
+  p.g_lo_row = T;
+  if (g16_lo) {
+    rc = make_tmap_f16(&tmG1, g16_lo, (uint64_t)T, (uint64_t)ldg, (uint64_t)ldg, AT_BKT);
+    if (rc) return PMG_ERR_UNSUPPORTED_SHAPE;
+    p.g_lo_row = 0;
+  }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((p.n_mtiles + 1) / 2, p.n_ntiles, p.splits);
   if (PA == 1 && fmt == 0) {
     PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    atb_tc_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(tmY, tmY1, tmG, p);
+    atb_tc_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(tmY, tmY1, tmG, tmG1, p);
   } else if (PA == 2 && fmt == 1) {
     PMG_CUDA_CHECK(cudaFuncSetAttribute(atb_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    atb_tc_kernel<2, 1><<<grid, TC_THREADS, smem, st>>>(tmY, tmY1, tmG, p);
+    atb_tc_kernel<2, 1><<<grid, TC_THREADS, smem, st>>>(tmY, tmY1, tmG, tmG1, p);
   } else {
     return PMG_ERR_BAD_ARG;
   }

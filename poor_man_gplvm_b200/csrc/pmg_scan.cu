@@ -85,6 +85,13 @@ struct BwdParams {
   float* tw_partial;
   float* beta_halo;
   float* beta_end;
+  // operands of the transition-count GEMM as bf16 hi/lo pieces, written in place of the fp32 r (bulk kernel only):
+  // row t of xa_* = alpha_t [2K], row t+1 of xr_* = r_{t+1} / z_t [2K]; leading dimension ld_x (elements)
+  uint16_t* xa_hi;
+  uint16_t* xa_lo;
+  uint16_t* xr_hi;
+  uint16_t* xr_lo;
+  int64_t ld_x;
 };
 
 template <int Q, int WPC, int WT>
@@ -723,6 +730,8 @@ constexpr int kRegWT = 10;   // compile-time half width of the register-window T
 #include "pmg_scan_bulk.cuh"
 namespace pmg {
 
+static bool wants_xi16(const FwdParams&) { return false; }
+static bool wants_xi16(const BwdParams& p) { return p.xa_hi != nullptr; }
 static bool bulk_ok(const FwdParams& p) {
   return (((uintptr_t)p.c.ll | (uintptr_t)p.alpha) & 15) == 0;
 }
@@ -753,6 +762,7 @@ static int dispatch(const P& p, int n_groups, cudaStream_t st) {
       else rc_ = bulk_launch<FWD, Qv, 10, 8, 2>(p, n_groups, st);                              \
       if (rc_ != PMG_ERR_UNSUPPORTED_SHAPE) return rc_;                                        \
     }                                                                                          \
+    if (wants_xi16(p)) return PMG_ERR_UNSUPPORTED_SHAPE;   /* only the bulk kernel writes them */ \
     if (reg) {                                                                                 \
       if constexpr (FWD) return launch_fwd<Qv, WPCv, kRegWT>(p, n_groups, st);                 \
       else return launch_bwd<Qv, WPCv, kRegWT>(p, n_groups, st);                               \
@@ -816,24 +826,59 @@ extern "C" int pmg_forward(const pmg_scan_plan* plan, const pmg_transition* tr, 
   return pmg::dispatch<true>(p, n_groups, (cudaStream_t)stream);
 }
 
-extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
-                            const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
-                            float* warm_out, float* gamma, float* gamma_lat,
-                            void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo,
-                            float* beta_end, int mode, const int* chain_ids, int n_ids,
-                            pmg_stream_t stream) {
+static int backward_impl(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                         const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
+                         float* warm_out, float* gamma, float* gamma_lat, void* gamma16, int64_t ldg, float* dyn_marg,
+                         float* r_out, void* xa_hi, void* xa_lo, void* xr_hi, void* xr_lo, int64_t ld_x,
+                         float* tw_partial, float* beta_halo, float* beta_end, int mode, const int* chain_ids, int n_ids,
+                         pmg_stream_t stream) {
   pmg::BwdParams p;
   int rc = pmg::fill_common(p.c, plan, tr, ll, ldll, mode, chain_ids, n_ids);
   if (rc) return rc;
   if (!alpha) return PMG_ERR_BAD_ARG;
   if (mode != 0 && !beta_end && !warm_in) return PMG_ERR_BAD_ARG;
   if (gamma16 && (ldg < tr->K || (ldg & 7))) return PMG_ERR_BAD_ARG;
+  if (xa_hi) {
+    if (!xa_lo || !xr_hi || !xr_lo || ld_x < 2 * tr->K || (ld_x & 7) || (tr->K & 7)) return PMG_ERR_BAD_ARG;
+    if (((uintptr_t)xa_hi | (uintptr_t)xa_lo | (uintptr_t)xr_hi | (uintptr_t)xr_lo) & 15) return PMG_ERR_ALIGNMENT;
+  }
   p.alpha = alpha; p.beta_in = beta_in; p.warm_in = warm_in; p.warm_stride = warm_stride; p.warm_out = warm_out;
   p.gamma = gamma; p.gamma_lat = gamma_lat; p.dyn_marg = dyn_marg;
   p.gamma16 = (__half*)gamma16; p.ldg = ldg;
   p.r_out = r_out; p.tw_partial = tw_partial; p.beta_halo = beta_halo; p.beta_end = beta_end;
+  p.xa_hi = (uint16_t*)xa_hi; p.xa_lo = (uint16_t*)xa_lo; p.xr_hi = (uint16_t*)xr_hi; p.xr_lo = (uint16_t*)xr_lo;
+  p.ld_x = ld_x;
   const int n_groups = mode == 1 ? n_ids : plan->n_chain;
   return pmg::dispatch<false>(p, n_groups, (cudaStream_t)stream);
+}
+
+extern "C" int pmg_backward(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                            const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
+                            float* warm_out, float* gamma, float* gamma_lat,
+                            void* gamma16, int64_t ldg, float* dyn_marg, float* r_out, float* tw_partial, float* beta_halo,
+                            float* beta_end, int mode, const int* chain_ids, int n_ids,
+                            pmg_stream_t stream) {
+  return backward_impl(plan, tr, ll, ldll, alpha, beta_in, warm_in, warm_stride, warm_out, gamma, gamma_lat, gamma16, ldg,
+                       dyn_marg, r_out, nullptr, nullptr, nullptr, nullptr, 0, tw_partial, beta_halo, beta_end, mode,
+                       chain_ids, n_ids, stream);
+}
+
+extern "C" int pmg_backward_xi16_supported(const pmg_transition* tr, float likelihood_scale) {
+  // the conditions under which dispatch<false> takes the bulk kernel (pointer alignment is checked at the call)
+  return tr && tr->kind == 0 && tr->W <= pmg::kRegWT && tr->K % 8 == 0 && tr->K <= 32 * 16 && likelihood_scale > 0.f;
+}
+
+extern "C" int pmg_backward_xi16(const pmg_scan_plan* plan, const pmg_transition* tr, const float* ll, int64_t ldll,
+                                 const float* alpha, const float* beta_in, const float* warm_in, int64_t warm_stride,
+                                 float* warm_out, float* gamma, float* gamma_lat, void* gamma16, int64_t ldg,
+                                 float* dyn_marg, void* xa_hi, void* xa_lo, void* xr_hi, void* xr_lo, int64_t ld_x,
+                                 float* tw_partial, float* beta_halo, float* beta_end, int mode, const int* chain_ids,
+                                 int n_ids, pmg_stream_t stream) {
+  if (!xa_hi) return PMG_ERR_BAD_ARG;
+  if (!pmg_backward_xi16_supported(tr, plan ? plan->likelihood_scale : 0.f)) return PMG_ERR_UNSUPPORTED_SHAPE;
+  return backward_impl(plan, tr, ll, ldll, alpha, beta_in, warm_in, warm_stride, warm_out, gamma, gamma_lat, gamma16, ldg,
+                       dyn_marg, nullptr, xa_hi, xa_lo, xr_hi, xr_lo, ld_x, tw_partial, beta_halo, beta_end, mode,
+                       chain_ids, n_ids, stream);
 }
 
 extern "C" int pmg_seam_check(int n, int len, const float* est, int64_t ld_est, const float* truth,

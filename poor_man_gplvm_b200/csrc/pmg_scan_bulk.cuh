@@ -12,6 +12,8 @@
 //     takes the warp reduction and the reciprocal off the loop-carried dependency chain.
 // Included by pmg_scan.cu (needs Geo, band_apply, chain_range, FwdParams, BwdParams).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "pmg_tc.cuh"
 
 namespace pmg {
@@ -278,6 +280,24 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
     }
     __syncwarp();
   };
+  // bf16 hi/lo pieces of a [K] row (operands of the transition-count GEMM, rounding as pmg_split_bf16): staged in
+  // the same shared row (KP bf16 hi | KP bf16 lo), written as 16-byte stores of consecutive lanes (K % 8 == 0)
+  auto store_row_bf16 = [&](uint16_t* dst_hi, uint16_t* dst_lo, const float (&v)[Q], float scale) {
+    __nv_bfloat16* th = reinterpret_cast<__nv_bfloat16*>(trow);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float f = v[q] * scale;
+      const __nv_bfloat16 h = __float2bfloat16_rn(f);
+      th[x0 + q] = h;
+      th[KP + x0 + q] = __float2bfloat16_rn(f - __bfloat162float(h));
+    }
+    __syncwarp();
+    for (int j = lane; j < K / 8; j += 32) {
+      reinterpret_cast<uint4*>(dst_hi)[j] = reinterpret_cast<const uint4*>(th)[j];
+      reinterpret_cast<uint4*>(dst_lo)[j] = reinterpret_cast<const uint4*>(th + KP)[j];
+    }
+    __syncwarp();
+  };
   for (int i = lane; i < 2 * exf; i += 32) exch[i] = 0.f;
   for (int i = lane; i < R * 3 * KP; i += 32) ring[i] = ((i / KP) % 3 == 0) ? -INFINITY : 0.f;
   if (lane == 0) {
@@ -429,6 +449,15 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
 #pragma unroll
       for (int q = 0; q < Q; ++q) { g0[q] = 0.f; g1[q] = 0.f; s0 += b0[q]; s1 += b1[q]; s2 = fmaf(Lc[q], b1[q], s2); }
     }
+    if (p.xa_hi && t < cr.t_end) {              // alpha_t as bf16 pieces, while its row is still in the ring
+      float av[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) av[q] = row[KP + q];
+      store_row_bf16(p.xa_hi + (size_t)t * p.ld_x, p.xa_lo + (size_t)t * p.ld_x, av, 1.f);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) av[q] = row[2 * KP + q];
+      store_row_bf16(p.xa_hi + (size_t)t * p.ld_x + K, p.xa_lo + (size_t)t * p.ld_x + K, av, 1.f);
+    }
     // all lanes are done with ring[slot]: refill it R steps ahead
     __syncwarp();
     if (lane == 0 && i + R < n_steps) {
@@ -480,6 +509,12 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_bulk_kernel(const BwdParams p,
         float* ro = p.r_out + (size_t)(t + 1) * 2 * K;
         store_row(ro, r0, r_scale);
         store_row(ro + K, r1, r_scale);
+      }
+      if (p.xr_hi && i != 0) {
+        uint16_t* rh = p.xr_hi + (size_t)(t + 1) * p.ld_x;
+        uint16_t* rl = p.xr_lo + (size_t)(t + 1) * p.ld_x;
+        store_row_bf16(rh, rl, r0, r_scale);
+        store_row_bf16(rh + K, rl + K, r1, r_scale);
       }
     } else if (t == cr.t_end && p.beta_halo) {
       float* o = p.beta_halo + (size_t)cr.s * 2 * K;

@@ -69,7 +69,7 @@ class EStepResult:
     """Tensors cover this rank's core bins only (views into the E-step buffers)."""
     __slots__ = ("ll", "alpha", "lmr", "gamma", "gamma_lat", "dyn_marg", "r", "tw", "log_marginal",
                  "n_relay_fwd", "n_relay_bwd", "n_fix_fwd", "n_fix_bwd", "seam_err_fwd", "seam_err_bwd", "plan",
-                 "alpha_ext", "r_ext", "core", "repaired", "halo")
+                 "alpha_ext", "r_ext", "core", "repaired", "halo", "xi16")
 
 
 class EStep:
@@ -203,6 +203,7 @@ class EStep:
         if self.tail.numel() != TAIL or self.tail.dtype != torch.float32 or not self.tail.is_contiguous():
             raise ValueError("tail must be a contiguous float32 view of %d entries" % TAIL)
         self.tail_host = torch.zeros(TAIL, dtype=torch.float32).pin_memory()
+        self._xbuf_f = self._xbuf_b = None          # message buffers of the boundary exchanges (time-sharded runs)
         self._sum_ws = None
         # which seams exist: forward seam c sits in front of chain c; backward seam c behind chain c
         self.f_lo = 0 if not self.shard.is_first else 1
@@ -240,58 +241,59 @@ class EStep:
     def _exchange_fwd(self, compact=False, nxt=None):
         """After a forward pass: the last true alpha goes right (seam truth of the neighbour's first
         chain) together with this pass's message at the bin where that chain's next warm-up starts; the first
-        true alpha goes left (normaliser of the neighbour's last backward seam)."""
-        if not self.shard.active:
+        true alpha goes left (normaliser of the neighbour's last backward seam).  One pack kernel, one all-gather of
+        the ranks' fixed-size buffers, one unpack kernel."""
+        sh = self.shard
+        if not sh.active:
             return
-        K2 = 2 * self.K
+        K = self.K
+        if self._xbuf_f is None:
+            self._xbuf_f = torch.zeros(8 * K, dtype=torch.float32, device=self.dev)
+            self._xbuf_b = torch.zeros(4 * K, dtype=torch.float32, device=self.dev)
         if compact:
-            first, last = self.first_out.reshape(-1), self.fwd_end[self.S - 1].reshape(-1)
+            first, last = self.first_out, self.fwd_end[self.S - 1]
         else:
-            first = self.alpha[self.core.start].reshape(-1)
-            last = self.alpha[self.core.stop - 1].reshape(-1)
+            first, last = self.alpha[self.core.start], self.alpha[self.core.stop - 1]
         # message at the bin in front of the right neighbour's first warm-up bin (of the NEXT pass).  The kernels'
         # slot S holds it only when that bin lies in the last chain's own range; with a ragged (short) last chunk
         # it lies in an earlier chain, so it is read back from the stored filtered posterior instead.
         t_star = self.core.stop - self.halos[1] - 1
+        kw = {}
         if nxt is None:
-            warm = torch.zeros_like(last)
+            pass
         elif t_star < self.core.start:
-            warm = self.fwarm[nxt][self.S].reshape(-1)
+            kw = dict(warm_src=self.fwarm[nxt][self.S])
         elif compact:
-            row = self.ll[t_star]
-            E = torch.exp2((row - row.max()) * (self.scale * 1.4426950408889634))
-            warm = torch.cat([self.ax[t_star, :self.K], self.ax[t_star, self.K] * E])
+            kw = dict(ax_row=self.ax[t_star], ll_row=self.ll[t_star])
         else:
-            warm = self.alpha[t_star].reshape(-1)
-        from_left, from_right = self.shard.boundary(torch.cat([first, torch.zeros_like(first)]),
-                                                    torch.cat([last, warm]))
-        if from_left is not None:
-            self.fwd_end_ext[0].copy_(from_left[:K2].view(2, self.K))
-            w = from_left[K2:]
-            if nxt is not None:
-                self.fwarm[nxt][0].copy_(w.view(2, self.K))
+            kw = dict(warm_src=self.alpha[t_star])
+        ops.boundary_pack_fwd(K, self._xbuf_f, first, last, scale=self.scale, **kw)
+        g = sh.neighbour_gather(self._xbuf_f)
+        from_left = g[sh.rank - 1, 4 * K:] if not sh.is_first else None
+        from_right = g[sh.rank + 1, :4 * K] if not sh.is_last else None
+        # what arrives: seam truth + warm start of chain 0; the neighbour's first message = the row behind the block
+        # (compact: alpha[0,:] and the scalar a1s with alpha[1,x] = a1s * exp2(s*log2e*(ll[x] - max ll)))
+        stop = {}
         if from_right is not None:
-            msg = from_right[:K2].view(2, self.K)
-            if compact:
-                # row of the compact buffer for the neighbour's first bin: alpha[0,:] and the scalar a1s with
-                # alpha[1,x] = a1s * exp2(s*log2e*(ll[x] - max ll))  (the factor the kernels recompute)
-                row = self.ll[self.core.stop]
-                E = torch.exp2((row - row.max()) * (self.scale * 1.4426950408889634))
-                self.ax[self.core.stop, :self.K] = msg[0]
-                self.ax[self.core.stop, self.K] = msg[1].sum() / E.sum()
-            else:
-                self.alpha[self.core.stop].copy_(msg)
+            stop = (dict(ax_stop=self.ax[self.core.stop], ll_stop=self.ll[self.core.stop]) if compact
+                    else dict(alpha_stop=self.alpha[self.core.stop]))
+        ops.boundary_unpack_fwd(K, from_left, from_right, self.fwd_end_ext[0],
+                                self.fwarm[nxt][0] if nxt is not None else None, scale=self.scale, **stop)
 
     def _exchange_bwd(self, nxt=None):
         """After a backward pass: beta at the first core bin goes left (seam truth of the neighbour's last
         chain) together with this pass's message at the bin where that chain's next warm-up starts."""
-        if not self.shard.active:
+        sh = self.shard
+        if not sh.active:
             return
         K2 = 2 * self.K
-        first = self.beta_end[0].reshape(-1)
-        warm = self.bwarm[nxt][0].reshape(-1) if nxt is not None else torch.zeros_like(first)
-        _, from_right = self.shard.boundary(torch.cat([first, warm]), None)
-        if from_right is not None:
+        buf = self._xbuf_b
+        buf[:K2].copy_(self.beta_end[0].reshape(-1))
+        if nxt is not None:
+            buf[K2:].copy_(self.bwarm[nxt][0].reshape(-1))
+        g = sh.neighbour_gather(buf)
+        if not sh.is_last:
+            from_right = g[sh.rank + 1]
             self.beta_end[self.S].copy_(from_right[:K2].view(2, self.K))
             if nxt is not None:
                 self.bwarm[nxt][self.S].copy_(from_right[K2:].view(2, self.K))
@@ -443,7 +445,7 @@ class EStep:
         self.halos = [nxt, new]
 
     def run(self, tuning, want_gamma=False, want_gamma_lat=True, want_dyn=False, want_r=False, gamma16=None,
-            before_sync=None, forward_only=False, graph_ok=False, want_tw=None):
+            before_sync=None, forward_only=False, graph_ok=False, want_tw=None, xi16_ok=False):
         """One E-step.  gamma16: optional [2,T,ldg] fp16 buffer (T = local bins incl. halos) that receives
         the hi/lo pieces of the latent posterior.  before_sync: optional callable invoked once both passes, the
         device repairs and the seam checks are enqueued, before the launching thread waits for the verdict (work
@@ -455,6 +457,9 @@ class EStep:
         want_tw: per-chain sums of the latent posterior (``res.tw``; general kernels only).  Default: only when no
         ``gamma16`` is requested -- with the fp16 pieces the statistics GEMM returns sum_t gamma through the column
         of ones of the counts.
+        xi16_ok: with ``want_r``, the caller accepts the transition-count operands as bf16 hi/lo pieces
+        (``res.xi16`` [4, T, 2K]: alpha hi/lo, r hi/lo; ``res.r_ext`` is then None) where the backward kernel can
+        write them itself -- two passes over [T,2K] arrays less than splitting the fp32 arrays afterwards.
         graph_ok: the caller vouches that ``tuning``, ``gamma16`` and everything ``before_sync`` touches are fixed
         buffers and that ``before_sync`` only enqueues GPU work (no Python state): the launch sequence may then be
         captured into a CUDA graph and replayed."""
@@ -471,8 +476,11 @@ class EStep:
         gamma = torch.empty((self.T, 2, K), **f32) if want_gamma else None
         gamma_lat = torch.empty((self.T, K), **f32) if want_gamma_lat else None
         dyn = torch.empty((self.T, 2), **f32) if want_dyn else None
-        r = None
-        if want_r:        # rows core.start+1 .. core.stop are written by the backward pass; row core.start is unused
+        r = xi16 = None
+        if want_r and xi16_ok and not compact and ops.xi16_supported(self.op, self.scale):
+            # every row the count GEMM reads is written by the pass (alpha: core rows; r: rows core.start+1 ..)
+            xi16 = torch.empty((4, self.T, 2 * K), dtype=torch.bfloat16, device=self.dev)
+        elif want_r:      # rows core.start+1 .. core.stop are written by the backward pass; row core.start is unused
             r = torch.empty((self.T, 2, K), **f32)
             r[:self.core.start + 1].zero_()
             r[self.core.stop:].zero_()
@@ -514,7 +522,7 @@ class EStep:
             ops.backward(self.plan, self.op, self.ll, self.alpha, gamma=gamma, gamma_lat=gamma_lat, dyn_marg=dyn,
                          r_out=r, tw_partial=(self.tw_partial if want_tw else None), beta_halo=self.beta_halo,
                          beta_end=self.beta_end,
-                         mode=mode, chain_ids=ids, gamma16=gamma16,
+                         mode=mode, chain_ids=ids, gamma16=gamma16, xi16=xi16,
                          warm_in=(b_in if mode == 0 else self.beta_halo), warm_out=b_out, halo_max=hmax_b, **sel)
 
         seams = S > 1 or self.shard.active
@@ -628,6 +636,7 @@ class EStep:
         res.ll, res.lmr = self.ll[c], lmr[c]
         res.alpha = None if compact else self.alpha[c]
         res.alpha_ext, res.r_ext = (None if compact else self.alpha), r
+        res.xi16 = xi16
         res.gamma = gamma[c] if gamma is not None else None
         res.gamma_lat = gamma_lat[c] if gamma_lat is not None else None
         res.dyn_marg = dyn[c] if dyn is not None else None

@@ -511,13 +511,26 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
              beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
-             warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0):
+             warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0, xi16=None):
+    """xi16: optional bf16 [4, T, 2K] (alpha hi, alpha lo, r hi, r lo) that receives the operands of the
+    transition-count GEMM as pieces instead of ``r_out`` (see xi16_supported)."""
     lib = _lib.load()
     _select(plan, mode, sel_err, sel_tol)
     tr = op.cstruct()
     n_ids = int(chain_ids.numel()) if chain_ids is not None else 0
     wp, ws = _warm(warm_in)
     dense = getattr(op, "dense", None)
+    if xi16 is not None:
+        if r_out is not None or xi16.dtype != torch.bfloat16 or xi16.dim() != 3 or xi16.shape[0] != 4:
+            raise ValueError("xi16 must be bfloat16 [4, T, 2K] and replaces r_out")
+        check(lib.pmg_backward_xi16(C.byref(plan), C.byref(tr), _p(ll), ll.shape[1], _p(alpha), _p(beta_in), wp, ws,
+                                    _p(warm_out), _p(gamma), _p(gamma_lat), _p(gamma16),
+                                    (gamma16.shape[2] if gamma16 is not None else 0), _p(dyn_marg), _p(xi16[0]),
+                                    _p(xi16[1]), _p(xi16[2]), _p(xi16[3]), xi16.shape[2], _p(tw_partial),
+                                    _p(beta_halo), _p(beta_end), int(mode), _p(chain_ids), n_ids, _stream()),
+              "pmg_backward_xi16")
+        _count(1)
+        return
     if mode == 0 and dense is not None:
         wk = dense.workspace(plan.n_chain, ll.device)
         check(lib.pmg_backward_dense(C.byref(plan), C.byref(tr), _p(dense.P16), dense.kb_ptr, int(halo_max), _p(ll),
@@ -567,6 +580,25 @@ def backward_compact(plan, op, ll, ax, gamma16, beta_halo=None, beta_end=None, b
                                    _p(beta_in), wp, ws, _p(warm_out), _p(gamma16), gamma16.shape[2],
                                    _p(beta_halo), _p(beta_end), int(mode), _p(chain_ids), n_ids,
                                    _stream()), "pmg_backward_compact")
+    _count(1)
+
+
+def boundary_pack_fwd(K, out, first, last, warm_src=None, ax_row=None, ll_row=None, scale=1.0):
+    """out [8K] <- [first | 0 | last | warm]; warm = warm_src [2K], or the compact row (ax_row, ll_row), or zeros."""
+    mode = 2 if ax_row is not None else (1 if warm_src is not None else 0)
+    check(_lib.load().pmg_boundary_pack_fwd(int(K), _p(first), _p(last), mode, _p(warm_src), _p(ax_row), _p(ll_row),
+                                            float(scale), _p(out), _stream()), "pmg_boundary_pack_fwd")
+    _count(1)
+
+
+def boundary_unpack_fwd(K, from_left, from_right, fwd_end0, fwarm0, ax_stop=None, ll_stop=None, scale=1.0,
+                        alpha_stop=None):
+    """from_left [4K] -> fwd_end0, fwarm0; from_right [4K] -> the row behind the block (compact: ax_stop + ll_stop)."""
+    if from_left is None and from_right is None:
+        return
+    check(_lib.load().pmg_boundary_unpack_fwd(int(K), _p(from_left), _p(from_right), _p(fwd_end0), _p(fwarm0),
+                                              int(ax_stop is not None), _p(ax_stop), _p(ll_stop), float(scale),
+                                              _p(alpha_stop), _stream()), "pmg_boundary_unpack_fwd")
     _count(1)
 
 
@@ -687,7 +719,7 @@ def split_bf16(src):
     return out
 
 
-XI_TC_MIN_BINS = int(os.environ.get("PMG_XI_TC_MIN_BINS", "4096"))
+XI_TC_MIN_BINS = 4096        # shorter recordings: the fp32 CUDA-core reduction (no piece rounding) is as fast
 
 
 def atb_bf16x2(A, B, out=None):
@@ -705,6 +737,36 @@ def atb_bf16x2(A, B, out=None):
     ws = _workspace(nbytes, A.device)
     check(lib.pmg_atb_bf16x2(T, M, N, _p(a16), a16.shape[2], _p(b16), b16.shape[2], _p(out), _p(ws), ws.numel(),
                              _stream()), "pmg_atb_bf16x2")
+    _count(2)
+    return out
+
+
+def xi16_supported(op, likelihood_scale):
+    """True when the backward pass can write the transition-count operands as bf16 pieces itself (bulk kernel)."""
+    if getattr(op, "dense", None) is not None:
+        return False
+    tr = op.cstruct()
+    return bool(_lib.load().pmg_backward_xi16_supported(C.byref(tr), float(likelihood_scale)))
+
+
+def atb_bf16x2_pieces(xi16, row0, n_rows, M=None, N=None, out=None):
+    """sum_t alpha_t^T (r_{t+1} / z_t) over the pairs t in [row0, row0 + n_rows) from the pieces of
+    backward(..., xi16=...): alpha rows [row0, row0+n) against r rows [row0+1, row0+n+1).  M, N: leading columns used
+    of the two operands (default all 2K; the latent-only families use the first K)."""
+    lib = _lib.load()
+    ld = xi16.shape[2]
+    M = ld if M is None else int(M)
+    N = ld if N is None else int(N)
+    T = int(n_rows)
+    a_hi, a_lo = xi16[0, row0:row0 + T], xi16[1, row0:row0 + T]
+    r_hi, r_lo = xi16[2, row0 + 1:row0 + 1 + T], xi16[3, row0 + 1:row0 + 1 + T]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=xi16.device)
+    nbytes = lib.pmg_atb_f16_workspace_bytes(T, M, N)
+    ws = _workspace(nbytes, xi16.device)
+    # operand roles of pmg_atb_bf16x2: out[k, n] = sum_t G[t, k] Y[t, n] with G = alpha, Y = r
+    check(lib.pmg_atb_bf16x2_pieces(T, M, N, _p(a_hi), _p(a_lo), ld, _p(r_hi), _p(r_lo), ld, _p(out), _p(ws),
+                                    ws.numel(), _stream()), "pmg_atb_bf16x2_pieces")
     _count(2)
     return out
 

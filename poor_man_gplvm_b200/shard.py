@@ -2,7 +2,7 @@
 
 Rank r owns a contiguous block of time bins.  The only exchanges of the EM hot path are
   * once per fit: ``halo`` rows of the spike matrix from each neighbour (warm-up bins of the scan),
-  * per pass: one boundary message (2K floats) to each neighbour,
+  * per pass: one boundary message (4K floats) to each neighbour (one all-gather of fixed-size buffers),
   * per EM iteration: one all-reduce of the packed sufficient statistics (K*N + K + 1 floats),
   * per seam-repair sweep: one scalar all-reduce (does any rank still have a failing seam?).
 The reference has no multi-device code; this layer is new.
@@ -95,6 +95,21 @@ class TimeShard:
         like = to_left if to_left is not None else to_right
         return self._exchange(to_left, to_right, like if to_right is not None else None,
                               like if to_left is not None else None)
+
+    def neighbour_gather(self, buf):
+        """All ranks' fixed-size message buffers, [world, n] on buf's device: ONE collective per pass -- its host cost
+        (a single enqueue) is a fraction of a batched send/recv group, and the payload (8K floats per rank) is noise on
+        NVSwitch.  Rank r reads rows r-1 and r+1."""
+        n = buf.numel()
+        key = (n, buf.device, buf.dtype)
+        out = self._gather_out.get(key) if hasattr(self, "_gather_out") else None
+        if out is None:
+            if not hasattr(self, "_gather_out"):
+                self._gather_out = {}
+            out = self._gather_out[key] = torch.empty((self.world, n), dtype=buf.dtype,
+                                                       device="cpu" if self.staged else buf.device)
+        dist.all_gather_into_tensor(out.view(-1), self._out(buf.reshape(-1)), group=self.group)
+        return out.to(buf.device) if self.staged else out
 
     def block_offset(self, T):
         """(first global bin of this rank's block, total number of bins) for a local block of T bins."""

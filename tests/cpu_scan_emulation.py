@@ -114,7 +114,7 @@ def forward(plan, op, ll, alpha, lmr, halo_state=None, carry_in=None, mode=0, ch
 
 def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_out=None, tw_partial=None,
              beta_halo=None, beta_end=None, beta_in=None, mode=0, chain_ids=None, gamma16=None, warm_in=None,
-             warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0):
+             warm_out=None, sel_err=None, sel_tol=0.0, halo_max=0, xi16=None):
     K, T = op.K, int(plan.T)
     P0 = _dense_move(op)
     M = op.M.reshape(2, 2).astype(np.float64)
@@ -185,6 +185,44 @@ def backward(plan, op, ll, alpha, gamma=None, gamma_lat=None, dyn_marg=None, r_o
                     dst[:] = be.astype(np.float32).reshape(-1)
         if tw_partial is not None:
             _np(tw_partial)[s] = tw.astype(np.float32)
+
+
+def boundary_pack_fwd(K, out, first, last, warm_src=None, ax_row=None, ll_row=None, scale=1.0):
+    """pmg_boundary_pack_fwd on host tensors: out [8K] = [first | 0 | last | warm]"""
+    o = _np(out)
+    K2 = 2 * K
+    o[:] = 0.0
+    if first is not None:
+        o[:K2] = _np(first).reshape(-1)
+    if last is not None:
+        o[2 * K2:3 * K2] = _np(last).reshape(-1)
+    if ax_row is not None:
+        a, l = _np(ax_row), _np(ll_row).astype(np.float64)
+        E = np.exp2((l - l.max()) * (scale * 1.4426950408889634))
+        o[3 * K2:3 * K2 + K] = a[:K]
+        o[3 * K2 + K:] = (a[K] * E).astype(np.float32)
+    elif warm_src is not None:
+        o[3 * K2:] = _np(warm_src).reshape(-1)
+
+
+def boundary_unpack_fwd(K, from_left, from_right, fwd_end0, fwarm0, ax_stop=None, ll_stop=None, scale=1.0,
+                        alpha_stop=None):
+    K2 = 2 * K
+    if from_left is not None:
+        fl = _np(from_left)
+        _np(fwd_end0).reshape(-1)[:] = fl[:K2]
+        if fwarm0 is not None:
+            _np(fwarm0).reshape(-1)[:] = fl[K2:2 * K2]
+    if from_right is not None:
+        fr = _np(from_right)
+        if ax_stop is not None:
+            l = _np(ll_stop).astype(np.float64)
+            E = np.exp2((l - l.max()) * (scale * 1.4426950408889634))
+            a = _np(ax_stop)
+            a[:K] = fr[:K]
+            a[K] = fr[K:K2].sum() / E.sum()
+        else:
+            _np(alpha_stop).reshape(-1)[:] = fr[:K2]
 
 
 def seam_check(n, length, est_ptr, ld_est, truth_ptr, ld_truth, err, floor_val=1e-12):

@@ -48,6 +48,7 @@ def _patch():
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     ops.forward, ops.backward, ops.seam_check = emu.forward, emu.backward, emu.seam_check
     ops.seam_check_fix = emu.seam_check_fix
+    ops.boundary_pack_fwd, ops.boundary_unpack_fwd = emu.boundary_pack_fwd, emu.boundary_unpack_fwd
     ops.strided_sum_workspace = lambda device: None
     ops.strided_sum = lambda src, dst, ws: dst.copy_(src.sum(dim=0, keepdim=True, dtype=torch.float64))
     ops.EmissionOperands = emu.FakeEmission

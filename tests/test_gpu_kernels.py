@@ -177,6 +177,22 @@ def test_forward_backward_matches_linear_oracle(ops, K, mv, custom, T, chunk_len
     xi = np.exp(log_acc.astype(np.float64))
     assert abs(xi.sum() - (T - 1)) < 1e-3 * (T - 1)
     assert np.max(np.abs(xi - want["xi"])) < 2e-4 * max(1.0, want["xi"].max())
+    # the same counts from bf16 hi/lo pieces written by the backward kernel itself (pmg_backward_xi16 +
+    # pmg_atb_bf16x2_pieces: decode_latent's path on long recordings) -- where the bulk kernel runs
+    if ops.xi16_supported(es.op, scale):
+        res2 = es.run(None, want_gamma=True, want_gamma_lat=True, want_dyn=True, want_r=True, xi16_ok=True)
+        assert res2.xi16 is not None and res2.r_ext is None
+        x16 = host(res2.xi16.float()).astype(np.float64)
+        a_rec, r_rec = x16[0] + x16[1], x16[2] + x16[3]
+        a_ref, r_ref = host(res.alpha).reshape(T, 2 * K), host(res.r).reshape(T, 2 * K)
+        assert np.max(np.abs(a_rec - a_ref)) <= 2.0 ** -16 * np.abs(a_ref).max() + 2e-6     # (second pass: warm starts)
+        assert np.max(np.abs(r_rec[1:] - r_ref[1:])) <= (2.0 ** -16 + 1e-5) * np.abs(r_ref).max()
+        G2 = host(ops.atb_bf16x2_pieces(res2.xi16, 0, T - 1))
+        Gh = host(G)
+        assert np.max(np.abs(G2 - Gh)) < 1e-4 * np.abs(Gh).max()
+        assert np.max(np.abs(host(res2.gamma) - host(res.gamma))) < 2e-6
+    else:
+        assert custom is not None or K % 8 or K > 512 or mv > 2.0
 
 
 DENSE_TC_CASES = [
