@@ -53,6 +53,20 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// reciprocal and logarithm on the special-function unit (one instruction each, ~1 ulp / 2^-22): the per-bin
+// normaliser only has to be positive and consistent (every step renormalises), and log c_t is added to s*max ll
+// (hundreds in magnitude: one fp32 ulp of the sum is 6e-5), so the IEEE sequences (9 and 35 instructions per bin,
+// the latter executed by the whole warp for lane 0's benefit) bought nothing
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float log_fast(float x) {
+  float y;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.6931471805599453f;
+}
 __device__ __forceinline__ float2 pk(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 pk1(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -91,12 +105,25 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b, int lane) {
 // either side come from the neighbouring lanes by rotating shuffles.  Lane 31 holds only padding (zeros;
 // the dispatch guarantees K <= 31*Q), so lane 0 receives the zeros that lie left of bin 0 and lane 30 the
 // zeros right of bin K-1; what lane 31 itself computes lands in padding and is never used.
+//
+// Packed FMAs need ALIGNED register pairs.  In the window w[0 .. Q+2WT) (w[WT+i] = this lane's entry i) the aligned
+// ("natural") pairs start at offsets s with s = WT (mod 2); output pair p under tap j reads the pair starting at
+// 2p + j, which is natural for only half of the taps -- and the compiler re-pairs the straddling operands with
+// register moves (75 per bin in the 11-tap kernel, as many as the FMAs themselves).  So the other half of the taps
+// accumulates into output pairs SHIFTED by one entry, so[p] = (out[2p-1], out[2p]), whose operands start at
+// 2p - 1 + j: natural again.  Every FMA operand is then a natural pair and the two partial sums meet in Q scalar adds:
+//   out[2p] = nat[p].x + so[p].y,   out[2p+1] = nat[p].y + so[p+1].x.
 template <int QP, int WT>
 __device__ __forceinline__ void band_pk(const float2 (&a)[QP], float2 (&out)[QP], const float (&tp)[2 * WT + 1],
                                         int lane_left, int lane_right) {
   constexpr int Q = 2 * QP;
   static_assert(WT <= Q, "band half width must not exceed the lane segment");
-  float w[Q + 2 * WT];
+  constexpr int NWIN = Q + 2 * WT;
+  constexpr int PAR = WT & 1;              // parity of the natural pair offsets
+  constexpr int S0 = PAR ? -1 : 0;         // first natural offset used (w[-1] and w[NWIN] do not exist: zeros that
+                                           // only reach the discarded halves of so[0] and so[QP])
+  constexpr int NP = (NWIN - S0 + 1) / 2;  // natural pairs N(S0), N(S0+2), ...
+  float w[NWIN];
 #pragma unroll
   for (int p = 0; p < QP; ++p) { w[WT + 2 * p] = a[p].x; w[WT + 2 * p + 1] = a[p].y; }
 #pragma unroll
@@ -104,13 +131,41 @@ __device__ __forceinline__ void band_pk(const float2 (&a)[QP], float2 (&out)[QP]
     w[WT - 1 - i] = __shfl_sync(0xffffffffu, w[WT + Q - 1 - i], lane_left);
     w[WT + Q + i] = __shfl_sync(0xffffffffu, w[WT + i], lane_right);
   }
+  float2 nat[NP];
 #pragma unroll
-  for (int p = 0; p < QP; ++p) {
-    float2 acc = mul2(pk1(tp[0]), pk(w[2 * p], w[2 * p + 1]));
-#pragma unroll
-    for (int j = 1; j <= 2 * WT; ++j) acc = fma2(pk1(tp[j]), pk(w[2 * p + j], w[2 * p + j + 1]), acc);
-    out[p] = acc;
+  for (int m = 0; m < NP; ++m) {
+    const int s = S0 + 2 * m;
+    if (s >= WT && s + 1 < WT + Q) nat[m] = a[(s - WT) / 2];
+    else nat[m] = pk(s >= 0 ? w[s >= 0 ? s : 0] : 0.f, s + 1 < NWIN ? w[s + 1 < NWIN ? s + 1 : 0] : 0.f);
   }
+  float2 so[QP + 1];
+  bool so_init = false;
+#pragma unroll
+  for (int j = 0; j <= 2 * WT; ++j) {
+    if ((j & 1) == PAR) continue;          // these taps are natural for the unshifted outputs
+    const float2 t2 = pk1(tp[j]);
+#pragma unroll
+    for (int p = 0; p <= QP; ++p) {
+      const float2 x = nat[(2 * p - 1 + j - S0) / 2];
+      so[p] = so_init ? fma2(t2, x, so[p]) : mul2(t2, x);
+    }
+    so_init = true;
+  }
+  bool nat_init = false;
+  float2 acc[QP];
+#pragma unroll
+  for (int j = 0; j <= 2 * WT; ++j) {
+    if ((j & 1) != PAR) continue;
+    const float2 t2 = pk1(tp[j]);
+#pragma unroll
+    for (int p = 0; p < QP; ++p) {
+      const float2 x = nat[(2 * p + j - S0) / 2];
+      acc[p] = nat_init ? fma2(t2, x, acc[p]) : mul2(t2, x);
+    }
+    nat_init = true;
+  }
+#pragma unroll
+  for (int p = 0; p < QP; ++p) out[p] = pk(acc[p].x + so[p].y, acc[p].y + so[p + 1].x);
 }
 
 template <int QP>
@@ -322,14 +377,14 @@ __global__ void __launch_bounds__(32 * NW, 1) fwd_c_kernel(const FwdCParams p, c
     warp_sum2(S0, S1, lane);
     S1 *= p1;
     const float cn = S0 + S1;                    // c_t = sum of prior x likelihood
-    const float inv = 1.f / cn;
+    const float inv = rcp_fast(cn);
 
     if (i >= i_begin) {
       float* ob = outb + (size_t)(og * NB + orow) * KP + x0;
       const float2 i2 = pk1(inv);
 #pragma unroll
       for (int q = 0; q < QP; ++q) *reinterpret_cast<float2*>(ob + 2 * q) = mul2(v0[q], i2);
-      if (lane == 0) *reinterpret_cast<float2*>(ax_row + K) = pk(p1 * inv_prev * inv, logf(cn) + c.scale * m);
+      if (lane == 0) *reinterpret_cast<float2*>(ax_row + K) = pk(p1 * inv_prev * inv, log_fast(cn) + c.scale * m);
       ax_row += p.ldax;
       ++orow;
       if (orow == NB || i == n_steps - 1) {
@@ -571,7 +626,7 @@ __global__ void __launch_bounds__(32 * NW, 1) bwd_c_kernel(const BwdCParams p, c
 
     float S0 = s0.x + s0.y, S2 = s2.x + s2.y;
     warp_sum2(S0, S2, lane);
-    const float inv = 1.f / (S0 + a1s * S2);
+    const float inv = rcp_fast(S0 + a1s * S2);
     const float2 i2 = pk1(inv);
 
     if (core) {

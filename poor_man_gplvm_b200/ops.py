@@ -358,7 +358,7 @@ def stationary_joint(P0, M):
 def dense_scan_pays(K, W):
     """The lockstep tensor-core scan costs ~3 K^2 tensor flops per bin and pass, a band kernel K (2W+1) CUDA-core
     flops: the GEMM form wins once the band covers a good part of the matrix."""
-    return K >= 256 and (2 * W + 1) * 4 >= K
+    return 256 <= K <= 4096 and (2 * W + 1) * 4 >= K        # (16 column tiles of 256: the kernel's limit)
 
 
 class DenseMoveTC:
