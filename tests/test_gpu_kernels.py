@@ -4,8 +4,13 @@ Tolerances: the oracle runs in fp64; the kernels compute in fp32 (linear space),
 so posteriors are compared at 1e-5 absolute (BASELINE.json north_star), log
 marginals at 1e-4 relative, emission log-likelihoods at a few fp32 ulps of |ll|.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 torch = pytest.importorskip("torch")
 
@@ -416,6 +421,45 @@ def test_atb_f16_tensor_core_matches_numpy(ops, T, K, N):
     assert np.max(np.abs(got - want)) < 2e-6 * np.max(np.abs(want)) + 1e-5
     ref32 = host(ops.atb(dev(G), dev(Y), impl=1))
     assert np.max(np.abs(got - ref32)) < 4e-6 * np.max(np.abs(want)) + 1e-5
+
+
+# ----------------------------------------------------------------------------- boundary exchange kernels
+@pytest.mark.parametrize("K", [24, 400, 2000])
+def test_boundary_pack_unpack_match_the_host_restatement(ops, K):
+    """pmg_boundary_pack_fwd / pmg_boundary_unpack_fwd (one kernel on each side of the time-sharded boundary
+    exchange) against the NumPy restatement the CPU orchestration tests run on (tests/cpu_scan_emulation.py)."""
+    import cpu_scan_emulation as emu
+    rng = np.random.default_rng(K)
+    scale = 0.8
+    first, last, warm = (rng.random(2 * K).astype(np.float32) for _ in range(3))
+    ax_row = np.concatenate([rng.random(K), [0.37, -3.0, 0.0, 0.0]]).astype(np.float32)
+    ll_row = (rng.standard_normal(K) * 4 - 30).astype(np.float32)
+    for kw in ({}, {"warm_src": warm}, {"ax_row": ax_row, "ll_row": ll_row}):
+        want = np.full(8 * K, 7.0, np.float32)
+        emu.boundary_pack_fwd(K, want, first, last, scale=scale, **kw)
+        got = torch.full((8 * K,), 7.0, device="cuda")
+        ops.boundary_pack_fwd(K, got, dev(first), dev(last), scale=scale, **{k: dev(v) for k, v in kw.items()})
+        assert np.allclose(host(got), want, rtol=2e-5, atol=1e-30), kw.keys()     # (fp32 exp2 of arguments down to -100)
+    from_left, from_right = rng.random(4 * K).astype(np.float32), rng.random(4 * K).astype(np.float32)
+    for compact in (False, True):
+        w_end, w_warm = np.zeros((2, K), np.float32), np.zeros((2, K), np.float32)
+        g_end, g_warm = torch.zeros((2, K), device="cuda"), torch.zeros((2, K), device="cuda")
+        if compact:
+            w_ax, g_ax = np.zeros(K + 4, np.float32), torch.zeros(K + 4, device="cuda")
+            emu.boundary_unpack_fwd(K, from_left, from_right, w_end, w_warm, ax_stop=w_ax, ll_stop=ll_row, scale=scale)
+            ops.boundary_unpack_fwd(K, dev(from_left), dev(from_right), g_end, g_warm, ax_stop=g_ax, ll_stop=dev(ll_row),
+                                    scale=scale)
+            assert np.allclose(host(g_ax), w_ax, rtol=2e-5)
+        else:
+            w_al, g_al = np.zeros(2 * K, np.float32), torch.zeros(2 * K, device="cuda")
+            emu.boundary_unpack_fwd(K, from_left, from_right, w_end, w_warm, alpha_stop=w_al)
+            ops.boundary_unpack_fwd(K, dev(from_left), dev(from_right), g_end, g_warm, alpha_stop=g_al)
+            assert np.array_equal(host(g_al), w_al)
+        assert np.array_equal(host(g_end), w_end) and np.array_equal(host(g_warm), w_warm)
+    # a rank at the edge of the recording: nothing arrives from that side, nothing is touched
+    g_end = torch.full((2, K), 5.0, device="cuda")
+    ops.boundary_unpack_fwd(K, None, None, g_end, None)
+    assert float(g_end.min()) == 5.0
 
 
 # ----------------------------------------------------------------------------- M-step
