@@ -180,10 +180,12 @@ class EStep:
             buf[S] = 1.0
         self.warm_cur = 0
         self.warm_valid = False
-        self.err = torch.zeros(2 * S, **f32)                       # final check of every seam
-        self.err1 = torch.zeros(2 * S, **f32)                      # first check of the interior seams (before repairs)
-        self.err_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
-        self.err1_host = torch.zeros(2 * S, dtype=torch.float32).pin_memory()
+        # seam errors: [final check of every seam | first check of the interior seams (before repairs)], one buffer so
+        # that one copy brings both to the host
+        self._errs = torch.zeros(4 * S, **f32)
+        self.err, self.err1 = self._errs[:2 * S], self._errs[2 * S:]
+        self._errs_host = torch.zeros(4 * S, dtype=torch.float32).pin_memory()
+        self.err_host, self.err1_host = self._errs_host[:2 * S], self._errs_host[2 * S:]
         # per-chain warm-up lengths (adaptive mode): [this pass, next pass] for each direction, device + host copies
         self.hf = self.hb = None
         if self.adaptive:
@@ -351,8 +353,7 @@ class EStep:
         elif self.shard.active:
             self.shard.allreduce_flat_sum_(self.tail)
         self.tail_host.copy_(self.tail, non_blocking=True)
-        self.err_host.copy_(self.err, non_blocking=True)
-        self.err1_host.copy_(self.err1, non_blocking=True)
+        self._errs_host.copy_(self._errs, non_blocking=True)
 
     def _verdict_wait(self):
         """The ONE synchronisation of an E-step."""

@@ -30,7 +30,15 @@ def phase(name):
         PHASE_HOOK(name)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device.  Every operator call needs it, ~16 times per EM
+    iteration: the raw getter costs ~1 us, building a torch.cuda.Stream object ~10 us -- at 125 000 bins per rank the
+    launching thread, not the GPU, was the bottleneck."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
