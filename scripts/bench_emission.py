@@ -1,5 +1,5 @@
-"""Times the emission GEMM alone at the headline shape (experiment knobs come from the environment)."""
-import sys, os, time
+"""Times the emission GEMM alone at the headline shape (CUDA events, repeated launches)."""
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from poor_man_gplvm_b200 import ops

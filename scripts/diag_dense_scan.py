@@ -4,7 +4,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from poor_man_gplvm_b200 import ops, gp_kernel as gpk
 from poor_man_gplvm_b200.estep import EStep
-from oracle import linear_ref as lin
 dev = torch.device("cuda")
 
 

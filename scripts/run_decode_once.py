@@ -2,7 +2,7 @@
 for the general scan kernels and the transition-count GEMM."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import poor_man_gplvm_b200 as pmg
 from poor_man_gplvm_b200.synthetic import make_dataset_torch
 T, N, K = int(os.environ.get("T", 1000000)), 500, 400
