@@ -420,3 +420,61 @@ def test_time_sharded_fit_em_on_cpu_matches_single_process():
     dyn = np.concatenate([three[r]["dyn"] for r in range(3)])
     assert np.max(np.abs(post - one["post"])) < 2e-5
     assert np.max(np.abs(dyn - one["dyn"])) < 2e-5
+
+
+def _dense_plan_worker(q):
+    """EStep with a lockstep-scan operand attached: chain plan sized to one wave of accumulator tiles, and the longest
+    warm-up of each pass handed to the (stand-in) scan operators as ``halo_max``."""
+    try:
+        emu = _patch()
+        from poor_man_gplvm_b200 import ops
+        from poor_man_gplvm_b200.estep import EStep
+        seen = []
+        fwd0, bwd0 = emu.forward, emu.backward
+
+        def fwd(*a, **k):
+            seen.append(("f", k.get("mode", 0), k.get("halo_max")))
+            return fwd0(*a, **k)
+
+        def bwd(*a, **k):
+            seen.append(("b", k.get("mode", 0), k.get("halo_max")))
+            return bwd0(*a, **k)
+
+        ops.forward, ops.backward = fwd, bwd
+        T, N, K = 4000, 8, 320
+        d, P, M, host = _problem(T, N, K, 3)
+        op = ops.MoveOperator(host, M, torch.device("cpu"), P0=P[0], dense_tc=True)
+        assert op.dense is not None and op.dense.n_ntiles == 2 and op.dense.chains(148) == 128 * 74
+        y = torch.from_numpy(d["y"].copy())
+        es = EStep(y, op, None, None, 1.0, halo=32, adaptive=True)
+        # 2 "SMs" (patched): one wave = 128 chains; 4000 bins / 128 chains < the 64-bin minimum chunk
+        plan = (es.S, es.chunk_len)
+        tun = torch.from_numpy(d["tuning_true"].astype(np.float32))
+        out = []
+        for _ in range(3):
+            res = es.run(tun, want_gamma=True, want_gamma_lat=True)
+            out.append((res.gamma.numpy().copy(), res.halo))
+        q.put(("ok", plan, seen, [o[1] for o in out], out[-1][0]))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put(("err", traceback.format_exc()))
+
+
+def test_lockstep_scan_plan_and_halo_max_plumbing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_dense_plan_worker, args=(q,))
+    p.start()
+    res = q.get(timeout=600)
+    p.join(timeout=60)
+    assert res[0] == "ok", res[1]
+    _, (S, chunk), seen, halos, gamma = res
+    assert chunk == 64 and S == (4000 + 63) // 64
+    # every mode-0 pass carries the longest per-chain warm-up of that pass (adaptive: base <= 32, boosts <= 32)
+    assert all(hm is not None and 0 < hm <= 32 for kind, mode, hm in seen if mode == 0), seen
+    assert {k for k, m, _ in seen if m == 0} == {"f", "b"}
+    from oracle import linear_ref as lin
+    d, P, M, host = _problem(4000, 8, 320, 3)
+    want = lin.e_step(d["y"], d["tuning_true"].astype(np.float64), P.astype(np.float64), M.astype(np.float64),
+                      np.ones(8), np.ones(320))
+    assert np.max(np.abs(gamma - want["gamma"])) < 2e-5
