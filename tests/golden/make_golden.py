@@ -38,6 +38,9 @@ CASES = {
     # spatio-temporal neuron mask [T,N] (decoder.py:291-294) and per-bin dt for naive Bayes (decoder.py:73-85)
     "mask_tn_dt": dict(N=11, K=32, T=120, ls=5.0, n_iter=2, m_step_maxiter=20, m_step_tol=-1.0, mask_tn=True,
                        dt_l=True, seed=7),
+    # dense custom transition kernel (gp_kernel.py:61-66): K = 256 puts the CUDA path on the lockstep tensor-core scan
+    "dense_custom": dict(N=16, K=256, T=400, ls=12.0, pmj=0.02, pjm=0.05, n_iter=2, m_step_maxiter=25,
+                         m_step_tol=-1.0, custom_kernel="dense", seed=12),
     # shortest recordings
     "t1": dict(N=5, K=16, T=1, ls=4.0, n_iter=1, m_step_maxiter=5, m_step_tol=-1.0, seed=9),
     "t2": dict(N=5, K=16, T=2, ls=4.0, n_iter=1, m_step_maxiter=5, m_step_tol=-1.0, seed=10),
@@ -59,6 +62,11 @@ def make_inputs(c):
         inp["ma_neuron"] = (rng.random((c["T"], c["N"])) < 0.8).astype(np.float32)
     if c.get("dt_l"):
         inp["dt_l"] = rng.uniform(0.5, 1.5, size=c["T"]).astype(np.float32)
+    if c.get("custom_kernel") == "dense":
+        x = np.arange(c["K"])
+        dist = np.abs(x[:, None] - x[None, :])
+        inp["custom_transition_kernel"] = (np.exp(-dist / 40.0) * (1 + 0.3 * rng.random((c["K"], c["K"]))) + 0.01
+                                           ).astype(np.float32)
     post = rng.random((c["T"], c["K"])).astype(np.float32) * np.float32(0.1)
     post = post / post.sum(axis=1, keepdims=True)
     inp["log_posterior_init"] = np.log(post)
@@ -68,9 +76,12 @@ def make_inputs(c):
 def run_case(name, c, ref, fdt):
     import jax.numpy as jnp
     inp, rng = make_inputs(c)
+    mk = {}
+    if "custom_transition_kernel" in inp:
+        mk["custom_transition_kernel"] = jnp.array(inp["custom_transition_kernel"])
     m = ref.core.PoissonGPLVMJump1D(n_neuron=c["N"], n_latent_bin=c["K"], tuning_lengthscale=c["ls"],
                                     movement_variance=c.get("mv", 1.0), p_move_to_jump=c.get("pmj", 0.01),
-                                    p_jump_to_move=c.get("pjm", 0.01))
+                                    p_jump_to_move=c.get("pjm", 0.01), **mk)
     basis = np.asarray(m.tuning_basis)
     params0 = rng.standard_normal((basis.shape[1], c["N"])).astype(np.float32)
     m.params = jnp.array(params0)
@@ -129,7 +140,8 @@ def run_case(name, c, ref, fdt):
     out["nb_argmax"] = np.argmax(np.asarray(nb["log_posterior_latent"]), axis=1).astype(np.int32)
     # transition matrices as the reference builds them
     P, logP, M, logM = ref.gpk.create_transition_prob_1d(m.possible_latent_bin, m.possible_dynamics,
-                                                         c.get("mv", 1.0), c.get("pmj", 0.01), c.get("pjm", 0.01))
+                                                         c.get("mv", 1.0), c.get("pmj", 0.01), c.get("pjm", 0.01),
+                                                         **({"custom_kernel": mk["custom_transition_kernel"]} if mk else {}))
     out["tr_P"], out["tr_logP"], out["tr_M"], out["tr_logM"] = A(P), A(logP), A(M), A(logM)
     out["meta_case"] = np.array(repr(c))
     # keep the fixtures small: for the README-sized cases the T-sized arrays are stored as float32 (6e-8
@@ -147,6 +159,14 @@ def run_case(name, c, ref, fdt):
                 elif a.dtype == np.float64:
                     out[k] = a.astype(np.float32)
         out["in_y"] = out["in_y"].astype(np.uint8)
+    if c.get("custom_kernel"):
+        # K x K x 2 x 2 outputs of a K = 256 model: keep what the tests read, in float32 where a tolerance allows
+        for k in ("dec_p_transition_full", "dec_log_joint_full", "dec_p_joint_full", "tr_logP", "tr_P",
+                  "dec_log_transition_latent", "dec_p_transition_latent", "dec_log_causal_posterior_all",
+                  "dec_log_likelihood_all", "nb_log_posterior_latent", "dec_log_transition_dynamics"):
+            out.pop(k, None)
+        for k in ("dec_log_accumulated_joint_total", "dec_p_joint_latent"):
+            out[k] = out[k].astype(np.float32)
     print("  %s [%s]: %.1f s, lml %s" % (name, np.dtype(fdt).name, time.time() - t0, out["em_log_marginal_l"][-1]),
           flush=True)
     return out
@@ -166,6 +186,8 @@ def main():
     for name, c in CASES.items():
         if only and name not in only:
             continue
+        if c.get("custom_kernel") and not x64:
+            continue                                # (fp64 fixture only: 3 MB)
         out = run_case(name, c, ref, fdt)
         np.savez_compressed(os.path.join(HERE, "%s_%s.npz" % (name, "f64" if x64 else "f32")), **out)
 

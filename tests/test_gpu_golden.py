@@ -22,8 +22,11 @@ def load(name, prec="f64"):
 
 def make_model(g, c):
     import poor_man_gplvm_b200 as pmg
+    mk = {}
+    if "in_custom_transition_kernel" in g:
+        mk["custom_transition_kernel"] = np.asarray(g["in_custom_transition_kernel"], dtype=np.float32)
     m = pmg.PoissonGPLVMJump1D(c["N"], c["K"], tuning_lengthscale=c["ls"], movement_variance=c.get("mv", 1.0),
-                               p_move_to_jump=c.get("pmj", 0.01), p_jump_to_move=c.get("pjm", 0.01))
+                               p_move_to_jump=c.get("pmj", 0.01), p_jump_to_move=c.get("pjm", 0.01), **mk)
     # the SVD basis is backend dependent (signs, near-degenerate pairs): inject the reference run's basis
     m.tuning_basis = np.asarray(g["tuning_basis"], dtype=np.float32)
     m.n_basis = m.tuning_basis.shape[1]
@@ -58,6 +61,35 @@ def test_fit_em_small_cases(name):
     check_em(got, g)
     assert got["m_step_res_l"]["n_iter"] == [int(v) for v in g["em_m_n_iter"]]
     assert np.allclose(got["m_step_res_l"]["final_loss"], g["em_m_final_loss"], rtol=1e-4)
+
+
+def test_dense_custom_kernel_on_the_lockstep_scan():
+    """A dense custom transition kernel (reference gp_kernel.py:61-66) at K = 256: fit_em and decode_latent run on the
+    lockstep tensor-core scan (pmg_forward_dense / pmg_backward_dense) and are held to the reference source's own
+    outputs at the north-star tolerances."""
+    from poor_man_gplvm_b200 import ops
+    g, c = load("dense_custom")
+    m = make_model(g, c)
+    assert m._transition_pack({})[4].dense is not None and ops.dense_scan_pays(c["K"], c["K"] - 1)
+    got = m.fit_em(g["in_y"].astype(np.float32), **em_kwargs(g, c))
+    check_em(got, g)
+    assert got["m_step_res_l"]["n_iter"] == [int(v) for v in g["em_m_n_iter"]]
+    kw = em_kwargs(g, c)
+    dec = m.decode_latent(g["in_y"].astype(np.float32), tuning=np.asarray(g["em_tuning"], dtype=np.float32),
+                          ma_neuron=kw["ma_neuron"], ma_latent=kw["ma_latent"])
+    ref_lml = float(g["dec_log_marginal_final"])
+    assert abs(dec["log_marginal_final"] - ref_lml) < 1e-4 * abs(ref_lml)
+    assert np.max(np.abs(dec["posterior_all"] - g["dec_posterior_all"])) < 1e-5
+    assert np.max(np.abs(dec["posterior_dynamics_marg"] - g["dec_posterior_dynamics_marg"])) < 1e-5
+    lmr = np.asarray(dec["log_one_step_predictive_marginals_all"])
+    assert np.max(np.abs(lmr - g["dec_log_one_step_predictive_marginals_all"])) < 1e-3
+    for k in ("p_joint_latent", "p_joint_dynamics", "p_transition_dynamics"):
+        assert np.max(np.abs(np.asarray(dec[k]) - g["dec_" + k])) < 2e-5, k
+    tup = m._decode_latent(g["in_y"].astype(np.float32), np.asarray(g["em_tuning"], dtype=np.float32), {},
+                           ma_neuron=kw["ma_neuron"], ma_latent=kw["ma_latent"])
+    acc, want = np.asarray(tup[4]), g["dec_log_accumulated_joint_total"]
+    big = want > np.log(1e-6)
+    assert np.max(np.abs(acc[big] - want[big])) < 1e-3
 
 
 def test_fit_em_readme_config_pinned_adam():

@@ -21,10 +21,13 @@ def load(name, prec):
 
 
 def make_oracle(g, c, dtype):
+    mk = {}
+    if "in_custom_transition_kernel" in g:
+        mk["custom_transition_kernel"] = g["in_custom_transition_kernel"]
     return ref.OraclePoissonGPLVMJump1D(c["N"], c["K"], tuning_lengthscale=c["ls"],
                                         movement_variance=c.get("mv", 1.0), p_move_to_jump=c.get("pmj", 0.01),
                                         p_jump_to_move=c.get("pjm", 0.01), dtype=dtype,
-                                        tuning_basis=g["tuning_basis"], params=g["in_params"])
+                                        tuning_basis=g["tuning_basis"], params=g["in_params"], **mk)
 
 
 def em_kwargs(g, c):
@@ -152,3 +155,18 @@ def test_linear_em_driver_step_schedule_reproduces_the_free_run():
     # (hundreds of Adam steps per M-step amplify the last-digit differences between the linear-space E-step and the
     # reference's log-space one: 3e-9 here, 1e-9 on the pinned 50-step run above)
     assert np.allclose(np.array(em["log_marginal_l"]), g["em_log_marginal_l"][:n], rtol=1e-7)
+
+
+def test_linear_em_driver_with_a_dense_custom_kernel_matches_reference_source():
+    """The oracle of the lockstep-scan GPU tests (oracle/linear_ref with a dense custom transition kernel, reference
+    gp_kernel.py:61-66) against the reference source's own run of that model (fixture `dense_custom`, K = 256)."""
+    from oracle import linear_ref as lin
+    g, c = load("dense_custom", "f64")
+    o = make_oracle(g, c, np.float64)
+    kw = em_kwargs(g, c)
+    kw.pop("n_time_per_chunk")
+    em = lin.fit_em_linear(o, g["in_y"].astype(np.float64), **kw)
+    assert np.allclose(np.array(em["log_marginal_l"]), g["em_log_marginal_l"], rtol=1e-9)
+    assert np.allclose(em["tuning"], g["em_tuning"], rtol=1e-6)
+    assert np.allclose(em["posterior"], g["em_posterior"], rtol=0, atol=1e-7)          # fixture stored in float32
+    assert em["m_step_n_iter"] == [int(v) for v in g["em_m_n_iter"]]
