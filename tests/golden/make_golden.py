@@ -41,6 +41,10 @@ CASES = {
     # dense custom transition kernel (gp_kernel.py:61-66): K = 256 puts the CUDA path on the lockstep tensor-core scan
     "dense_custom": dict(N=16, K=256, T=400, ls=12.0, pmj=0.02, pjm=0.05, n_iter=2, m_step_maxiter=25,
                          m_step_tol=-1.0, custom_kernel="dense", seed=12),
+    # BASELINE.json configs[3] shape (N=500, K=400) on a recording just long enough for the production kernels
+    # (cta_group::2 emission units of 512 bins, tensor-core statistics, 125-CTA M-step, compact scans): EM outputs only
+    "headline_shape": dict(N=500, K=400, T=640, ls=10.0, n_iter=2, m_step_maxiter=20, m_step_tol=-1.0, seed=21,
+                           em_only=True, x64_only=True),
     # shortest recordings
     "t1": dict(N=5, K=16, T=1, ls=4.0, n_iter=1, m_step_maxiter=5, m_step_tol=-1.0, seed=9),
     "t2": dict(N=5, K=16, T=2, ls=4.0, n_iter=1, m_step_maxiter=5, m_step_tol=-1.0, seed=10),
@@ -110,7 +114,8 @@ def run_case(name, c, ref, fdt):
     out["em_m_final_error"] = np.array([float(v) for v in em["m_step_res_l"]["final_error"]], dtype=fdt)
     out["em_m_loss_history0"] = A(em["m_step_res_l"]["loss_history"][0])
     if c.get("em_only"):
-        for k in ("em_posterior",):
+        for k in ("em_posterior",) + (("em_tuning", "tuning_init", "tuning_basis", "em_posterior_latent_marg",
+                                       "em_m_loss_history0") if c.get("x64_only") else ()):
             out[k] = out[k].astype(np.float32)
         out["in_y"] = out["in_y"].astype(np.uint8)
         out["meta_case"] = np.array(repr(c))
@@ -186,8 +191,8 @@ def main():
     for name, c in CASES.items():
         if only and name not in only:
             continue
-        if c.get("custom_kernel") and not x64:
-            continue                                # (fp64 fixture only: 3 MB)
+        if (c.get("custom_kernel") or c.get("x64_only")) and not x64:
+            continue                                # (fp64 fixture only: a few MB)
         out = run_case(name, c, ref, fdt)
         np.savez_compressed(os.path.join(HERE, "%s_%s.npz" % (name, "f64" if x64 else "f32")), **out)
 

@@ -170,3 +170,18 @@ def test_linear_em_driver_with_a_dense_custom_kernel_matches_reference_source():
     assert np.allclose(em["tuning"], g["em_tuning"], rtol=1e-6)
     assert np.allclose(em["posterior"], g["em_posterior"], rtol=0, atol=1e-7)          # fixture stored in float32
     assert em["m_step_n_iter"] == [int(v) for v in g["em_m_n_iter"]]
+
+
+def test_linear_em_driver_at_the_headline_shape_matches_reference_source():
+    """oracle/linear_ref at N=500, K=400 (fixture `headline_shape`: the reference source's own fp64 run, T=640, two EM
+    iterations): the oracle the real-shape GPU tests trust is pinned at that shape too."""
+    from oracle import linear_ref as lin
+    g, c = load("headline_shape", "f64")
+    o = make_oracle(g, c, np.float64)
+    kw = em_kwargs(g, c)
+    kw.pop("n_time_per_chunk")
+    em = lin.fit_em_linear(o, g["in_y"].astype(np.float64), **kw)
+    assert np.allclose(np.array(em["log_marginal_l"]), g["em_log_marginal_l"], rtol=1e-9)
+    assert np.allclose(em["tuning"], g["em_tuning"], rtol=2e-6)                        # fixture stored in float32
+    assert np.allclose(em["posterior"], g["em_posterior"], rtol=0, atol=1e-6)
+    assert em["m_step_n_iter"] == [20, 20]
